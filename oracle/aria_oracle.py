@@ -1,0 +1,375 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement ("port") of the reference Aria forward.
+
+This file is the *oracle* for the parity tests, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py`.  Nothing under `aria_b200/` may import it: the product path has
+no CPU fallback.
+
+It restates, function by function, what the reference (rhymes-ai/Aria @ 9b25fecb, `/root/reference`)
+computes on the hot path, as plain torch CPU code over an explicit state-dict with the Hugging Face
+weight names.  Each function cites the reference file:line it follows.  Where the reference reaches
+into a third-party package that is not under /root/reference, the package + version is named:
+
+  * LM attention / RMSNorm / RoPE / decoder wiring : transformers (reference pins 4.46.3,
+    pyproject.toml:13; checked here against the installed 5.5.0 `LlamaAttention` eager path)
+  * ViT                                              : transformers Idefics2VisionTransformer
+  * projector attention                              : torch.nn.MultiheadAttention (torch 2.5.1 pinned)
+  * expert GEMM                                      : grouped_gemm==0.1.6 — the reference's own
+    `sequential_gemm` (moe_lm.py:398-428) is a full restatement and is what we follow.
+
+Parity pinning: the reference ships NO golden vectors / model-forward tests.  This oracle
+is pinned instead against outputs of the reference modules themselves, run in the build container by
+`oracle/make_golden.py` (fixtures in tests/golden/, checked by tests/test_oracle_golden.py and, when
+/root/reference is present, live by tests/test_oracle_vs_reference.py).
+
+Rounding follows the reference exactly: every torch op on a bf16 tensor rounds its result to bf16
+(e.g. fc1 -> bf16, silu -> bf16, product -> bf16), softmax statistics are fp32.
+
+Tie rule for top-k: the reference calls `torch.topk` (moe_lm.py:261) whose tie order is unspecified.
+The oracle (and the CUDA kernel) define it: among equal logits the LOWEST expert index wins, and
+selected experts are returned in descending-logit order (ties: ascending index).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------
+# MoE block  (aria/model/moe_lm.py)
+# ----------------------------------------------------------------------------------------------
+def router_gating(x: Tensor, w_router: Tensor) -> Tensor:
+    """moe_lm.py:190-201 `TopKRouter.gating`: logits = F.linear(x, W[E,d]) in the input dtype."""
+    return F.linear(x, w_router)
+
+
+def topk_lowest_index(logits: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """moe_lm.py:261 `torch.topk(logits, k, dim=1)` with the tie rule made explicit (see header)."""
+    vals, idx = torch.sort(logits.float(), dim=1, descending=True, stable=True)
+    return vals[:, :k].to(logits.dtype), idx[:, :k]
+
+
+def router_routing(logits: Tensor, k: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """moe_lm.py:243-273 eval path: topk -> softmax(fp32)->dtype -> per-expert histogram."""
+    top_logits, top_idx = topk_lowest_index(logits, k)
+    scores = torch.softmax(top_logits, dim=-1, dtype=torch.float32).type_as(logits)
+    counts = torch.bincount(top_idx.flatten(), minlength=logits.shape[1])  # == histc, :264-269
+    return scores, top_idx, counts
+
+
+def token_permutation(x: Tensor, top_idx: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """moe_lm.py:313-334: stable argsort of the flattened expert ids; rows = x[order // k]."""
+    flat = top_idx.flatten()
+    order = torch.argsort(flat, stable=True)
+    return x.index_select(0, order // k), order
+
+
+def sequential_gemm(inp: Tensor, weight: Tensor, counts: Tensor) -> Tensor:
+    """moe_lm.py:398-428: per-expert matmul over contiguous row groups, weight [E, in, out]."""
+    out = torch.zeros(inp.shape[0], weight.shape[-1], dtype=inp.dtype)
+    off = 0
+    for e in range(weight.shape[0]):
+        n = int(counts[e])
+        if n:
+            out[off : off + n] = inp[off : off + n] @ weight[e]
+        off += n
+    return out
+
+
+def glu(x: Tensor) -> Tensor:
+    """moe_lm.py:505-507: first half is the gate (silu), second half the up projection."""
+    a, b = torch.chunk(x, 2, dim=-1)
+    return F.silu(a) * b
+
+
+def grouped_mlp(permuted: Tensor, fc1: Tensor, fc2: Tensor, counts: Tensor) -> Tensor:
+    """moe_lm.py:511-525 `GroupedMLP.forward`."""
+    h = sequential_gemm(permuted, fc1, counts)
+    h = glu(h)
+    return sequential_gemm(h, fc2, counts)
+
+
+def token_unpermutation(y: Tensor, order: Tensor, scores: Tensor, k: int) -> Tensor:
+    """moe_lm.py:336-365: scatter rows back, scale by scores (bf16 multiply), sum over k."""
+    buf = torch.zeros((scores.numel(), y.shape[1]), dtype=y.dtype)
+    buf.index_copy_(0, order, y)
+    buf = buf.reshape(-1, k, y.shape[1])
+    buf = buf * scores.unsqueeze(-1)
+    return buf.sum(dim=1).type_as(y)
+
+
+def shared_expert_mlp(x: Tensor, gate_w: Tensor, up_w: Tensor, down_w: Tensor) -> Tensor:
+    """moe_lm.py:368-395 -> LlamaMLP.forward: down(silu(gate(x)) * up(x)), no bias."""
+    return F.linear(F.silu(F.linear(x, gate_w)) * F.linear(x, up_w), down_w)
+
+
+def moe_layer(x: Tensor, w: Dict[str, Tensor], k: int, prefix: str = "", return_parts: bool = False):
+    """moe_lm.py:548-577 `MoELayer.forward`.  `w` uses the reference parameter names:
+    router.weight [E,d], experts.fc1.weight [E,d,2I], experts.fc2.weight [E,I,d],
+    shared_experts.{gate,up,down}_proj.weight."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    logits = router_gating(x2, w[prefix + "router.weight"])
+    scores, top_idx, counts = router_routing(logits, k)
+    permuted, order = token_permutation(x2, top_idx, k)
+    y = grouped_mlp(permuted, w[prefix + "experts.fc1.weight"], w[prefix + "experts.fc2.weight"], counts)
+    out = token_unpermutation(y, order, scores, k).view(shape)
+    shared = shared_expert_mlp(
+        x,
+        w[prefix + "shared_experts.gate_proj.weight"],
+        w[prefix + "shared_experts.up_proj.weight"],
+        w[prefix + "shared_experts.down_proj.weight"],
+    )
+    out = out + shared  # moe_lm.py:576 `output += shared_expert_output`
+    if return_parts:
+        return out, dict(logits=logits, scores=scores, top_idx=top_idx, counts=counts, order=order,
+                         permuted=permuted, expert_out=y, shared=shared)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# LM decoder layer  (moe_lm.py:580-636 wiring; arithmetic from transformers modeling_llama)
+# ----------------------------------------------------------------------------------------------
+def rms_norm(x: Tensor, weight: Tensor, eps: float) -> Tensor:
+    """LlamaRMSNorm.forward (used at moe_lm.py:599-602,631): fp32 statistics, cast, then * weight."""
+    dt = x.dtype
+    h = x.to(torch.float32)
+    var = h.pow(2).mean(-1, keepdim=True)
+    h = h * torch.rsqrt(var + eps)
+    return weight * h.to(dt)
+
+
+def rope_cos_sin(position_ids: Tensor, head_dim: int, theta: float, dtype) -> Tuple[Tensor, Tensor]:
+    """LlamaRotaryEmbedding.forward (moe_lm.py:632): fp32 angles, cos/sin cast to the model dtype."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    freqs = position_ids[:, :, None].float() * inv_freq[None, None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def rotate_half(x: Tensor) -> Tensor:
+    x1 = x[..., : x.shape[-1] // 2]
+    x2 = x[..., x.shape[-1] // 2 :]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rope(q: Tensor, k: Tensor, cos: Tensor, sin: Tensor) -> Tuple[Tensor, Tensor]:
+    """apply_rotary_pos_emb, rotate-half convention (HF path; gptfast uses interleaved)."""
+    cos = cos.unsqueeze(1)
+    sin = sin.unsqueeze(1)
+    return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+
+
+def attention_core(q: Tensor, k: Tensor, v: Tensor, scaling: float, add_mask: Optional[Tensor]) -> Tensor:
+    """transformers `eager_attention_forward`: softmax(q k^T * s + mask) in fp32 -> dtype, @ v.
+    q [B,H,Tq,D], k/v [B,H,Tk,D]; returns [B,Tq,H,D]."""
+    w = torch.matmul(q, k.transpose(2, 3)) * scaling
+    if add_mask is not None:
+        w = w + add_mask
+    w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+    return torch.matmul(w, v).transpose(1, 2).contiguous()
+
+
+def causal_additive_mask(tq: int, tk: int, dtype) -> Tensor:
+    """Causal mask for queries occupying the LAST tq positions of tk keys."""
+    i = torch.arange(tq)[:, None] + (tk - tq)
+    j = torch.arange(tk)[None, :]
+    m = torch.zeros(tq, tk, dtype=dtype)
+    m.masked_fill_(j > i, torch.finfo(dtype).min)
+    return m[None, None]
+
+
+def lm_attention(x: Tensor, w: Dict[str, Tensor], prefix: str, n_heads: int, theta: float,
+                 position_ids: Tensor, past_kv: Optional[Tuple[Tensor, Tensor]] = None):
+    """LlamaAttention.forward selected at moe_lm.py:594 (MHA, no bias): q/k/v proj -> RoPE ->
+    cache append -> causal softmax attention -> o_proj.  Returns (out, (k_cache, v_cache))."""
+    B, T, d = x.shape
+    hd = d // n_heads
+    q = F.linear(x, w[prefix + "q_proj.weight"]).view(B, T, n_heads, hd).transpose(1, 2)
+    k = F.linear(x, w[prefix + "k_proj.weight"]).view(B, T, n_heads, hd).transpose(1, 2)
+    v = F.linear(x, w[prefix + "v_proj.weight"]).view(B, T, n_heads, hd).transpose(1, 2)
+    cos, sin = rope_cos_sin(position_ids, hd, theta, x.dtype)
+    q, k = apply_rope(q, k, cos, sin)
+    if past_kv is not None:
+        k = torch.cat([past_kv[0], k], dim=2)
+        v = torch.cat([past_kv[1], v], dim=2)
+    mask = causal_additive_mask(T, k.shape[2], x.dtype) if T > 1 else None
+    o = attention_core(q, k, v, hd ** -0.5, mask).reshape(B, T, d)
+    return F.linear(o, w[prefix + "o_proj.weight"]), (k, v)
+
+
+def moe_decoder_layer(x: Tensor, w: Dict[str, Tensor], prefix: str, cfg, position_ids: Tensor,
+                      past_kv=None):
+    """LlamaDecoderLayer.forward with mlp=MoELayer (moe_lm.py:590-602)."""
+    r = x
+    h = rms_norm(x, w[prefix + "input_layernorm.weight"], cfg["rms_norm_eps"])
+    h, kv = lm_attention(h, w, prefix + "self_attn.", cfg["num_attention_heads"], cfg["rope_theta"],
+                         position_ids, past_kv)
+    x = r + h
+    r = x
+    h = rms_norm(x, w[prefix + "post_attention_layernorm.weight"], cfg["rms_norm_eps"])
+    h = moe_layer(h, w, cfg["moe_topk"], prefix + "mlp.")
+    return r + h, kv
+
+
+def lm_forward(inputs_embeds: Tensor, w: Dict[str, Tensor], cfg, prefix: str = "language_model.",
+               past=None, num_logits_to_keep: int = 0):
+    """AriaMoELMForCausalLM.forward (moe_lm.py:605-661): layers -> final RMSNorm -> lm_head."""
+    B, T, _ = inputs_embeds.shape
+    past_len = 0 if past is None else past[0][0].shape[2]
+    position_ids = (torch.arange(T) + past_len)[None].expand(B, T)
+    x = inputs_embeds
+    new_past = []
+    for i in range(cfg["num_hidden_layers"]):
+        x, kv = moe_decoder_layer(x, w, f"{prefix}model.layers.{i}.", cfg, position_ids,
+                                  None if past is None else past[i])
+        new_past.append(kv)
+    x = rms_norm(x, w[prefix + "model.norm.weight"], cfg["rms_norm_eps"])
+    if num_logits_to_keep:
+        x = x[:, -num_logits_to_keep:, :]
+    return F.linear(x, w[prefix + "lm_head.weight"]), new_past
+
+
+# ----------------------------------------------------------------------------------------------
+# ViT  (aria/model/vision_encoder.py + transformers Idefics2VisionTransformer)
+# ----------------------------------------------------------------------------------------------
+def patch_attention_mask(pixel_mask: Tensor, patch: int) -> Tensor:
+    """vision_encoder.py:132-145: a patch is valid iff any of its pixels is."""
+    sub = pixel_mask.unfold(1, patch, patch).unfold(2, patch, patch)
+    return (sub.sum(dim=(-1, -2)) > 0).bool()
+
+
+def vit_position_ids(pmask: Tensor, n_side: int, dtype) -> Tensor:
+    """Idefics2VisionEmbeddings.forward: NaViT bucketised fractional coordinates -> position ids."""
+    B, Hp, Wp = pmask.shape
+    boundaries = torch.arange(1 / n_side, 1.0, 1 / n_side)
+    pos = torch.zeros(B, Hp * Wp, dtype=torch.long)
+    nb_h = pmask[:, :, 0].sum(dim=1)
+    nb_w = pmask[:, 0, :].sum(dim=1)
+    fh = torch.arange(Hp, dtype=torch.float32)[None, :] * (1.0 / nb_h)[:, None]
+    fw = torch.arange(Wp, dtype=torch.float32)[None, :] * (1.0 / nb_w)[:, None]
+    fh = torch.clamp(fh, max=1.0 - 1e-6).to(dtype)
+    fw = torch.clamp(fw, max=1.0 - 1e-6).to(dtype)
+    bh = torch.bucketize(fh, boundaries, right=True)
+    bw = torch.bucketize(fw, boundaries, right=True)
+    ids = (bh[:, :, None] * n_side + bw[:, None, :]).reshape(B, -1)
+    flat = pmask.view(B, -1)
+    pos[flat] = ids[flat]
+    return pos
+
+
+def vit_forward(pixel_values: Tensor, pixel_mask: Optional[Tensor], w: Dict[str, Tensor], vcfg,
+                prefix: str = "vision_tower.vision_model."):
+    """AriaVisionModel.forward (vision_encoder.py:94-130) over AriaVisionTransformer (:58-67: no
+    post-layernorm).  Returns (last_hidden_state [B,N,d], image_attn_mask [B,N] bool, True = pad)."""
+    P = vcfg["patch_size"]
+    B = pixel_values.shape[0]
+    dt = pixel_values.dtype
+    if pixel_mask is None:
+        pmask = torch.ones(B, pixel_values.shape[2] // P, pixel_values.shape[3] // P, dtype=torch.bool)
+    else:
+        pmask = patch_attention_mask(pixel_mask, P)
+    x = F.conv2d(pixel_values, w[prefix + "embeddings.patch_embedding.weight"],
+                 w[prefix + "embeddings.patch_embedding.bias"], stride=P)
+    x = x.flatten(2).transpose(1, 2)
+    pos = vit_position_ids(pmask, vcfg["image_size"] // P, dt)
+    x = x + F.embedding(pos, w[prefix + "embeddings.position_embedding.weight"])
+    flat = pmask.view(B, -1)
+    add_mask = None
+    if not bool(flat.all()):
+        add_mask = torch.zeros(B, 1, 1, flat.shape[1], dtype=dt)
+        add_mask.masked_fill_(~flat[:, None, None, :], torch.finfo(dt).min)
+    H = vcfg["num_attention_heads"]
+    d = x.shape[-1]
+    hd = d // H
+    eps = vcfg["layer_norm_eps"]
+    N = x.shape[1]
+    for i in range(vcfg["num_hidden_layers"]):
+        p = f"{prefix}encoder.layers.{i}."
+        r = x
+        h = F.layer_norm(x, (d,), w[p + "layer_norm1.weight"], w[p + "layer_norm1.bias"], eps)
+        q = F.linear(h, w[p + "self_attn.q_proj.weight"], w[p + "self_attn.q_proj.bias"])
+        k = F.linear(h, w[p + "self_attn.k_proj.weight"], w[p + "self_attn.k_proj.bias"])
+        v = F.linear(h, w[p + "self_attn.v_proj.weight"], w[p + "self_attn.v_proj.bias"])
+        q = q.view(B, N, H, hd).transpose(1, 2)
+        k = k.view(B, N, H, hd).transpose(1, 2)
+        v = v.view(B, N, H, hd).transpose(1, 2)
+        o = attention_core(q, k, v, hd ** -0.5, add_mask).reshape(B, N, d)
+        o = F.linear(o, w[p + "self_attn.out_proj.weight"], w[p + "self_attn.out_proj.bias"])
+        x = r + o
+        r = x
+        h = F.layer_norm(x, (d,), w[p + "layer_norm2.weight"], w[p + "layer_norm2.bias"], eps)
+        h = F.linear(h, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])
+        h = F.gelu(h, approximate="tanh")  # gelu_pytorch_tanh
+        h = F.linear(h, w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
+        x = r + h
+    return x, torch.logical_not(flat)  # vision_encoder.py:147-152
+
+
+# ----------------------------------------------------------------------------------------------
+# Projector  (aria/model/projector.py)
+# ----------------------------------------------------------------------------------------------
+def gelu_new(x: Tensor) -> Tensor:
+    """transformers ACT2FN['gelu_new'] (projector.py:40)."""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
+
+
+def projector_forward(x: Tensor, image_attn_mask: Optional[Tensor], w: Dict[str, Tensor], pcfg,
+                      prefix: str = "multi_modal_projector."):
+    """AriaProjector.forward (projector.py:160-189) incl. CrossAttention (:73-102) and FFN (:42-45).
+    nn.MultiheadAttention math: second in-projection (with bias) of q/k/v, scaled dot-product with a
+    boolean key mask (True = not allowed), out_proj."""
+    B, N, _ = x.shape
+    E = pcfg["embed_dim"]
+    H = pcfg["num_heads"]
+    hd = E // H
+    Q = pcfg["patch_to_query_dict"][N]
+    queries = w[prefix + "query"][:Q].unsqueeze(0).repeat(B, 1, 1)
+    ca = prefix + "cross_attn."
+    nq = F.layer_norm(queries, (E,), w[ca + "layer_norm.weight"], w[ca + "layer_norm.bias"], 1e-5)
+    query = F.linear(nq, w[ca + "q_proj.weight"])
+    xk = F.layer_norm(x, (x.shape[-1],), w[ca + "ln_kv.weight"], w[ca + "ln_kv.bias"], 1e-5)
+    key = F.linear(xk, w[ca + "k_proj.weight"])
+    value = F.linear(xk, w[ca + "v_proj.weight"])
+    wi, bi = w[ca + "multihead_attn.in_proj_weight"], w[ca + "multihead_attn.in_proj_bias"]
+    q2 = F.linear(query, wi[:E], bi[:E]).view(B, Q, H, hd).transpose(1, 2)
+    k2 = F.linear(key, wi[E : 2 * E], bi[E : 2 * E]).view(B, N, H, hd).transpose(1, 2)
+    v2 = F.linear(value, wi[2 * E :], bi[2 * E :]).view(B, N, H, hd).transpose(1, 2)
+    # torch MHA: q scaled by 1/sqrt(hd) before the matmul (baddbmm path); softmax in the model dtype
+    # for the math path.  We keep fp32 softmax statistics -> dtype, which bounds both.
+    add_mask = None
+    if image_attn_mask is not None:
+        add_mask = torch.zeros(B, 1, 1, N, dtype=x.dtype)
+        add_mask.masked_fill_(image_attn_mask[:, None, None, :], float("-inf"))
+    o = attention_core(q2, k2, v2, hd ** -0.5, add_mask).reshape(B, Q, E)
+    o = F.linear(o, w[ca + "multihead_attn.out_proj.weight"], w[ca + "multihead_attn.out_proj.bias"])
+    o = F.linear(o, w[ca + "linear.weight"], w[ca + "linear.bias"])
+    h = F.layer_norm(o, (E,), w[prefix + "ln_ffn.weight"], w[prefix + "ln_ffn.bias"], 1e-5)
+    h = gelu_new(F.linear(h, w[prefix + "ffn.linear_in.weight"]))
+    return F.linear(h, w[prefix + "ffn.linear_out.weight"])
+
+
+# ----------------------------------------------------------------------------------------------
+# Full model  (aria/model/modeling_aria.py:194-335)
+# ----------------------------------------------------------------------------------------------
+def aria_forward(input_ids: Tensor, pixel_values: Optional[Tensor], pixel_mask: Optional[Tensor],
+                 w: Dict[str, Tensor], cfg, num_logits_to_keep: int = 0):
+    """AriaForConditionalGeneration.forward: embed -> ViT -> projector -> masked_scatter merge -> LM."""
+    tcfg = cfg["text_config"]
+    emb = F.embedding(input_ids, w["language_model.model.embed_tokens.weight"])
+    if pixel_values is not None:
+        feats, img_mask = vit_forward(pixel_values, pixel_mask, w, cfg["vision_config"])
+        feats = projector_forward(feats, img_mask if pixel_mask is not None else None, w, cfg["projector"])
+        n_tok = int((input_ids == cfg["image_token_index"]).sum())
+        if n_tok != feats.shape[0] * feats.shape[1]:
+            raise ValueError(  # modeling_aria.py:268-271
+                f"Image features and image tokens do not match: tokens: {n_tok}, "
+                f"features {feats.shape[0] * feats.shape[1]}")
+        m = (input_ids == cfg["image_token_index"]).unsqueeze(-1).expand_as(emb)
+        emb = emb.masked_scatter(m, feats.to(emb.dtype))
+    logits, past = lm_forward(emb, w, tcfg, num_logits_to_keep=num_logits_to_keep)
+    return logits, past

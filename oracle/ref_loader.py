@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference modules from /root/reference.
+
+Used only by `oracle/make_golden.py` (golden-vector generation, in the build container) and by
+`tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent, e.g. on the GPU box).
+Nothing in `aria_b200/` may import this file.
+
+Harness: the reference package cannot be imported as a package under the installed
+transformers 5.5 (`aria/model/__init__.py` pulls in processors whose imports moved), so we
+  1. register stub packages `aria`, `aria.model` so `__init__.py` is skipped,
+  2. provide `LLAMA_ATTENTION_CLASSES` (removed upstream; reference uses it at moe_lm.py:594),
+  3. load the five model files by path.
+Two lines of the reference cannot execute on CPU and are shimmed *outside* the reference files:
+  - moe_lm.py:264 `torch.histc` on int64 (no CPU kernel)  -> cast to float and back
+  - moe_lm.py:483 `torch.cuda.set_device(cpu tensor)`     -> no-op
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("ARIA_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "aria", "model", "moe_lm.py"))
+
+
+_loaded = {}
+
+
+def load_reference():
+    """Returns a namespace with the reference modules: moe_lm, vision_encoder, projector,
+    configuration_aria, modeling_aria."""
+    if _loaded:
+        return types.SimpleNamespace(**_loaded)
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+
+    import transformers.models.llama.modeling_llama as ml
+
+    if not hasattr(ml, "LLAMA_ATTENTION_CLASSES"):
+        ml.LLAMA_ATTENTION_CLASSES = {
+            k: ml.LlamaAttention for k in ("eager", "sdpa", "flash_attention_2")
+        }
+
+    # CPU shims (see module docstring)
+    if not getattr(torch.histc, "_aria_shim", False):
+        _histc = torch.histc
+
+        def histc(inp, bins=100, min=0, max=0, **kw):
+            if not inp.is_floating_point():
+                return _histc(inp.float(), bins=bins, min=min, max=max, **kw).to(torch.int64)
+            return _histc(inp, bins=bins, min=min, max=max, **kw)
+
+        histc._aria_shim = True
+        torch.histc = histc
+    if not torch.cuda.is_available():
+        torch.cuda.set_device = lambda *_a, **_k: None
+
+    for name in ("aria", "aria.model"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF_ROOT, *name.split("."))]
+            sys.modules[name] = m
+
+    for mod in ("moe_lm", "vision_encoder", "projector", "configuration_aria", "modeling_aria"):
+        full = f"aria.model.{mod}"
+        spec = importlib.util.spec_from_file_location(
+            full, os.path.join(REF_ROOT, "aria", "model", mod + ".py")
+        )
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+        _loaded[mod] = m
+    return types.SimpleNamespace(**_loaded)

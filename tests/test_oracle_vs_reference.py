@@ -1,0 +1,35 @@
+"""CPU, build container only: run the UNMODIFIED reference (/root/reference) live next to the oracle.
+Skipped on the GPU box, where the reference tree does not exist (the golden fixtures cover it there)."""
+import pytest
+import torch
+
+from oracle import aria_oracle as O
+from oracle import configs as C
+from oracle.ref_loader import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T,E,k", [(1, 8, 2), (7, 8, 2), (64, 16, 6), (33, 64, 6)])
+def test_moe_layer_live(dtype, T, E, k):
+    ref = load_reference()
+    tc = dict(hidden_size=128, moe_num_experts=E, moe_topk=k, moe_intermediate_size=64, moe_num_shared_experts=2)
+    gen = torch.Generator().manual_seed(T * 131 + E)
+    sd = {n: v.to(dtype) for n, v in C.moe_layer_state(tc, gen).items()}
+    x = torch.randn(1, T, 128, generator=gen).to(dtype)
+    layer = ref.moe_lm.MoELayer(ref.moe_lm.AriaMoELMConfig(**tc))
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.to(dtype).eval()
+    want = layer(x)
+    got, parts = O.moe_layer(x, sd, k, return_parts=True)
+    _, ridx, _ = layer.router(x)
+    if torch.equal(ridx.sort(1).values, parts["top_idx"].sort(1).values):
+        tol = 1e-6 if dtype == torch.float32 else 0.0
+        assert (want.float() - got.float()).abs().max() <= tol
+    else:  # a bf16 tie resolved differently by torch.topk: only tied rows may differ
+        vals = parts["logits"].float().sort(1, descending=True).values
+        tied = vals[:, k - 1] == vals[:, k]
+        bad = (want.float() - got.float()).abs().amax(-1).view(-1) > 0
+        assert not (bad & ~tied).any()
