@@ -1,0 +1,285 @@
+// MoE routing / dispatch kernels (HBM-bound integer + row-copy work; no tensor cores by design).
+//   route_from_logits  : torch.topk + softmax(fp32)->bf16 + histc      (aria/model/moe_lm.py:261-269)
+//   build_permutation  : argsort(stable) of the flattened expert ids  (moe_lm.py:329) as a counting sort
+//   permute_rows       : index_select of token rows                    (moe_lm.py:330)
+//   unpermute_combine  : zeros/index_copy_/mul/sum (+ shared add)      (moe_lm.py:350-364, :576)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace aria {
+
+constexpr int MAX_E = 64;
+constexpr int MAX_K = 8;
+
+// One warp per token. Each lane owns experts {lane, lane+32}.  Selection = k rounds of warp arg-max with the
+// tie rule "lowest expert id" (oracle/aria_oracle.py header).
+__global__ void __launch_bounds__(256) route_kernel(const __nv_bfloat16* __restrict__ logits, int32_t* __restrict__ top_idx,
+                                                    __nv_bfloat16* __restrict__ scores, int32_t* __restrict__ counts,
+                                                    int64_t T, int E, int k) {
+  __shared__ int hist[MAX_E];
+  for (int i = threadIdx.x; i < MAX_E; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * warps_per_block;
+  for (int64_t t = warp_global; t < T; t += warp_stride) {
+    const __nv_bfloat16* row = logits + t * E;
+    float v0 = lane < E ? __bfloat162float(row[lane]) : -INFINITY;
+    float v1 = lane + 32 < E ? __bfloat162float(row[lane + 32]) : -INFINITY;
+    bool used0 = lane >= E, used1 = lane + 32 >= E;
+    float sel_v = 0.f;  // lane j holds the j-th selected logit
+    int sel_i = 0;
+    for (int j = 0; j < k; ++j) {
+      float bv;
+      int bi;
+      // local best (lower index wins ties: candidate 0 has the lower index)
+      if (!used0 && (used1 || v0 >= v1)) {
+        bv = v0;
+        bi = lane;
+      } else if (!used1) {
+        bv = v1;
+        bi = lane + 32;
+      } else {
+        bv = -INFINITY;
+        bi = 0x7fffffff;
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (bi == lane) used0 = true;
+      if (bi == lane + 32) used1 = true;
+      if (lane == j) {
+        sel_v = bv;
+        sel_i = bi;
+      }
+    }
+    // softmax over the k selected logits in fp32 (moe_lm.py:262), max = first selected
+    const float vmax = __shfl_sync(0xffffffffu, sel_v, 0);
+    float e = lane < k ? expf(sel_v - vmax) : 0.f;
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s += __shfl_sync(0xffffffffu, e, j);
+    if (lane < k) {
+      top_idx[t * k + lane] = sel_i;
+      scores[t * k + lane] = __float2bfloat16_rn(e / s);
+      atomicAdd(&hist[sel_i], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
+// Stable counting sort, one block per expert: dest_row[i] = offsets[e] + #{i' < i : id[i'] == e}.
+__global__ void __launch_bounds__(1024) permutation_kernel(const int32_t* __restrict__ top_idx,
+                                                           const int32_t* __restrict__ counts,
+                                                           int32_t* __restrict__ offsets, int32_t* __restrict__ dest_row,
+                                                           int32_t* __restrict__ src_token, int64_t n, int E, int k) {
+  const int e = blockIdx.x;
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < e; ++i) acc += counts[i];
+    base_s = acc;
+    if (e == 0) {
+      int a = 0;
+      for (int i = 0; i < E; ++i) {
+        offsets[i] = a;
+        a += counts[i];
+      }
+      offsets[E] = a;
+    }
+  }
+  __syncthreads();
+  int running = base_s;
+  for (int64_t start = 0; start < n; start += blockDim.x) {
+    const int64_t i = start + threadIdx.x;
+    const bool hit = i < n && top_idx[i] == e;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    // 32 warps: every thread sums the (tiny) array
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      const int c = warp_cnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (hit) {
+      const int r = running + before + __popc(m & ((1u << lane) - 1));
+      dest_row[i] = r;
+      src_token[r] = static_cast<int32_t>(i / k);
+    }
+    running += total;
+    __syncthreads();
+  }
+}
+
+// permuted[r] = x[src_token[r]]; one warp per row, 128-bit loads/stores.
+__global__ void __launch_bounds__(256) permute_rows_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ src_token,
+                                                           uint4* __restrict__ out, int64_t rows, int vec_per_row) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
+       r += static_cast<int64_t>(gridDim.x) * wpb) {
+    const uint4* src = x + static_cast<int64_t>(src_token[r]) * vec_per_row;
+    uint4* dst = out + r * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) dst[v] = __ldg(src + v);
+  }
+}
+
+// out[t] = bf16( sum_j bf16(y[dest[t*k+j]] * s[t,j]) ) (+ shared[t] with one more bf16 rounding).
+__global__ void __launch_bounds__(256) combine_kernel(const uint4* __restrict__ y, const int32_t* __restrict__ dest_row,
+                                                      const __nv_bfloat16* __restrict__ scores, const uint4* __restrict__ shared_out,
+                                                      uint4* __restrict__ out, int64_t T, int vec_per_row, int k) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
+       t += static_cast<int64_t>(gridDim.x) * wpb) {
+    int rows[MAX_K];
+    float sc[MAX_K];
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) {
+      if (j < k) {
+        rows[j] = dest_row[t * k + j];
+        sc[j] = __bfloat162float(scores[t * k + j]);
+      }
+    }
+    for (int v = lane; v < vec_per_row; v += 32) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAX_K; ++j) {
+        if (j < k) {
+          const uint4 q = __ldg(y + static_cast<int64_t>(rows[j]) * vec_per_row + v);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[2 * i] += bf16r(bf16_lo(w[i]) * sc[j]);
+            acc[2 * i + 1] += bf16r(bf16_hi(w[i]) * sc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = bf16r(acc[i]);
+      if (shared_out) {
+        const uint4 q = __ldg(shared_out + t * vec_per_row + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += bf16_lo(w[i]);
+          acc[2 * i + 1] += bf16_hi(w[i]);
+        }
+      }
+      out[t * vec_per_row + v] =
+          make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+    }
+  }
+}
+
+__global__ void offsets_from_counts_kernel(const int64_t* counts, int32_t* offsets, int G) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int a = 0;
+    for (int i = 0; i < G; ++i) {
+      offsets[i] = a;
+      a += static_cast<int>(counts[i]);
+    }
+    offsets[G] = a;
+  }
+}
+
+static inline int grid_for_warps(int64_t n_warps, int wpb) {
+  int64_t blocks = (n_warps + wpb - 1) / wpb;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace aria
+
+using namespace aria;
+
+extern "C" int aria_route_from_logits(const void* logits, int32_t* top_idx, void* scores, int32_t* counts, int64_t T,
+                                      int32_t E, int32_t k, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(logits && top_idx && scores && counts);
+  ARIA_CHECK_ARG(E >= 1 && E <= MAX_E && k >= 1 && k <= MAX_K && k <= E && T >= 0);
+  if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * E, stream) != cudaSuccess) return ARIA_ERR_CUDA;
+  if (T == 0) return ARIA_OK;
+  route_kernel<<<grid_for_warps(T, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), top_idx,
+                                                         static_cast<__nv_bfloat16*>(scores), counts, T, E, k);
+  return check_launch("route_kernel");
+}
+
+extern "C" int aria_router_topk(const void* x, const void* w_router, void* logits_out, int32_t* top_idx, void* scores,
+                                int32_t* counts, int64_t T, int32_t d, int32_t E, int32_t k, aria_stream_t stream) {
+  ARIA_CHECK_ARG(x && w_router && logits_out);
+  ARIA_CHECK_ARG(E % 8 == 0);
+  if (T == 0) return aria_route_from_logits(logits_out, top_idx, scores, counts, 0, E, k, stream);
+  // gating (moe_lm.py:200): logits = F.linear(x, W) -> bf16, on the tensor cores
+  aria_gemm_desc_t g{};
+  g.a = x;
+  g.lda = d;
+  g.m = T;
+  g.n = E;
+  g.k = d;
+  g.b[0] = w_router;
+  g.n_seg = 1;
+  g.b_layout = ARIA_B_NK;
+  g.num_groups = 1;
+  g.epilogue = ARIA_EPI_LINEAR;
+  g.out[0] = logits_out;
+  g.ldo = E;
+  int rc = aria_gemm(&g, stream);
+  if (rc) return rc;
+  return aria_route_from_logits(logits_out, top_idx, scores, counts, T, E, k, stream);
+}
+
+extern "C" int aria_build_permutation(const int32_t* top_idx, const int32_t* counts, int32_t* offsets, int32_t* dest_row,
+                                      int32_t* src_token, int64_t T, int32_t E, int32_t k, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(top_idx && counts && offsets && dest_row && src_token);
+  ARIA_CHECK_ARG(E >= 1 && k >= 1 && T >= 0 && T * k < (1ll << 31));
+  permutation_kernel<<<E, 1024, 0, stream>>>(top_idx, counts, offsets, dest_row, src_token, T * k, E, k);
+  return check_launch("permutation_kernel");
+}
+
+extern "C" int aria_permute_rows(const void* x, const int32_t* src_token, void* permuted, int64_t rows, int32_t d,
+                                 aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(x && src_token && permuted && d % 8 == 0 && rows >= 0);
+  if (rows == 0) return ARIA_OK;
+  permute_rows_kernel<<<grid_for_warps(rows, 8), 256, 0, stream>>>(static_cast<const uint4*>(x), src_token,
+                                                                   static_cast<uint4*>(permuted), rows, d / 8);
+  return check_launch("permute_rows_kernel");
+}
+
+extern "C" int aria_unpermute_combine(const void* y, const int32_t* dest_row, const void* scores, const void* shared,
+                                      void* out, int64_t T, int32_t d, int32_t k, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(y && dest_row && scores && out && d % 8 == 0 && k >= 1 && k <= MAX_K && T >= 0);
+  if (T == 0) return ARIA_OK;
+  combine_kernel<<<grid_for_warps(T, 8), 256, 0, stream>>>(static_cast<const uint4*>(y), dest_row,
+                                                           static_cast<const __nv_bfloat16*>(scores),
+                                                           static_cast<const uint4*>(shared), static_cast<uint4*>(out), T,
+                                                           d / 8, k);
+  return check_launch("combine_kernel");
+}
+
+extern "C" int aria_offsets_from_counts(const int64_t* counts, int32_t* offsets, int32_t num_groups, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(counts && offsets && num_groups >= 1);
+  offsets_from_counts_kernel<<<1, 32, 0, stream>>>(counts, offsets, num_groups);
+  return check_launch("offsets_from_counts_kernel");
+}

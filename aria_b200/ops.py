@@ -1,0 +1,317 @@
+"""Torch-facing wrappers over the C ABI: tensors in, tensors out, raw pointers underneath.
+
+PyTorch is used for device memory and streams only; every computation below is one of our CUDA kernels.
+All wrappers launch on the current stream of the input's device and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype=bf16):
+    if not t.is_cuda:
+        raise RuntimeError("aria_b200 ops need CUDA tensors (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("expected a contiguous tensor")
+    if t.data_ptr() % 16:
+        raise RuntimeError("expected 16-byte aligned storage")
+    return t
+
+
+# ------------------------------------------------------------------------------------------- GEMMs
+def _run_gemm(d: L.GemmDesc, ref: torch.Tensor, what: str):
+    with torch.cuda.device(ref.device):
+        L.check(L.load().aria_gemm(C.byref(d), _stream(ref)), what)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = L.ACT_NONE,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear(x, weight, bias) -> act -> (+ residual); x [..., K], weight [N, K] (nn.Linear layout)."""
+    _chk(x), _chk(weight)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=bf16, device=x.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = x2.data_ptr(), K, M, N, K
+    d.b[0] = weight.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_NK, 1
+    d.epilogue, d.act = L.EPI_LINEAR, act
+    if bias is not None:
+        d.bias[0] = _chk(bias).data_ptr()
+    if residual is not None:
+        r2 = _chk(residual).reshape(-1, N)
+        d.residual, d.ldr = r2.data_ptr(), N
+    d.out[0], d.ldo = out.data_ptr(), N
+    _run_gemm(d, x, "linear")
+    return out.view(*x.shape[:-1], N)
+
+
+def linear_swiglu(x: torch.Tensor, gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """silu(x @ gate_w.T) * (x @ up_w.T) in one GEMM (LlamaMLP front half, moe_lm.py:368-395)."""
+    _chk(x), _chk(gate_w), _chk(up_w)
+    K = x.shape[-1]
+    N = gate_w.shape[0]
+    x2 = x.reshape(-1, K)
+    M = x2.shape[0]
+    out = torch.empty((M, N), dtype=bf16, device=x.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = x2.data_ptr(), K, M, N, K
+    d.b[0], d.b[1] = gate_w.data_ptr(), up_w.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 2, L.B_NK, 1
+    d.epilogue = L.EPI_SWIGLU
+    d.out[0], d.ldo = out.data_ptr(), N
+    _run_gemm(d, x, "linear_swiglu")
+    return out.view(*x.shape[:-1], N)
+
+
+def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu: bool = False,
+                 dbg=(0, 0, 0)) -> torch.Tensor:
+    """out[off[e]:off[e+1]] = a[off[e]:off[e+1]] @ b[e]; b [E, K, N] (GroupedGEMM.weight, moe_lm.py:465).
+    swiglu=True fuses `glu` (moe_lm.py:505-507): b has 2I columns, out has I."""
+    _chk(a), _chk(b), _chk(offsets, torch.int32)
+    rows, K = a.shape
+    E, Kb, Nb = b.shape
+    assert Kb == K and offsets.numel() == E + 1
+    N = Nb // 2 if swiglu else Nb
+    out = torch.empty((rows, N), dtype=bf16, device=a.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = a.data_ptr(), K, rows, N, K
+    d.b[0] = b.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GKN, E
+    d.group_offsets = offsets.data_ptr()
+    d.epilogue = L.EPI_SWIGLU if swiglu else L.EPI_LINEAR
+    d.out[0], d.ldo = out.data_ptr(), N
+    d.dbg_lbo, d.dbg_sbo, d.dbg_kadv = dbg
+    _run_gemm(d, a, "grouped_gemm")
+    return out
+
+
+def qkv_heads(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+              outs: Sequence[torch.Tensor], head_dim: int, rows_per_batch: int, pos0: int = 0, rope_mask: int = 0,
+              rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
+              position_ids: Optional[torch.Tensor] = None):
+    """Fused q/k/v projections: x [B*T, K] @ W_s.T (+bias) (+RoPE) scattered into head-major buffers
+    outs[s] [B, H, T_max, head_ld] at token offset pos0 (HF KV-cache layout)."""
+    _chk(x)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.k = x2.data_ptr(), K, x2.shape[0], K
+    d.n = weights[0].shape[0]
+    d.n_seg, d.b_layout, d.num_groups = len(weights), L.B_NK, 1
+    d.epilogue = L.EPI_HEADS
+    o0 = outs[0]
+    for s, (w, b, o) in enumerate(zip(weights, biases, outs)):
+        _chk(w), _chk(o)
+        assert w.shape[0] == d.n and o.shape[1:] == o0.shape[1:] and o.stride() == o0.stride()
+        d.b[s] = w.data_ptr()
+        d.out[s] = o.data_ptr()
+        if b is not None:
+            d.bias[s] = _chk(b).data_ptr()
+    d.head_dim, d.head_ld = head_dim, o0.shape[-1]
+    d.rows_per_batch, d.pos0 = rows_per_batch, pos0
+    d.stride_b, d.stride_h = o0.stride(0), o0.stride(1)
+    d.rope_mask = rope_mask
+    if rope_mask:
+        d.rope_cos, d.rope_sin = _chk(rope_cos).data_ptr(), _chk(rope_sin).data_ptr()
+    if position_ids is not None:
+        d.position_ids = _chk(position_ids, torch.int32).data_ptr()
+    _run_gemm(d, x, "qkv_heads")
+
+
+# ------------------------------------------------------------------------------------------- MoE routing
+def router_topk(x: torch.Tensor, w_router: torch.Tensor, k: int):
+    _chk(x), _chk(w_router)
+    T, dm = x.shape
+    E = w_router.shape[0]
+    dev = x.device
+    logits = torch.empty((T, E), dtype=bf16, device=dev)
+    idx = torch.empty((T, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((T, k), dtype=bf16, device=dev)
+    counts = torch.empty((E,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().aria_router_topk(_p(x), _p(w_router), _p(logits), _p(idx), _p(scores), _p(counts), T, dm, E, k,
+                                          _stream(x)), "router_topk")
+    return scores, idx, counts, logits
+
+
+def route_from_logits(logits: torch.Tensor, k: int):
+    _chk(logits)
+    T, E = logits.shape
+    dev = logits.device
+    idx = torch.empty((T, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((T, k), dtype=bf16, device=dev)
+    counts = torch.empty((E,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().aria_route_from_logits(_p(logits), _p(idx), _p(scores), _p(counts), T, E, k, _stream(logits)),
+                "route_from_logits")
+    return scores, idx, counts
+
+
+def build_permutation(top_idx: torch.Tensor, counts: torch.Tensor):
+    _chk(top_idx, torch.int32), _chk(counts, torch.int32)
+    T, k = top_idx.shape
+    E = counts.numel()
+    dev = top_idx.device
+    offsets = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+    dest = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    src = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().aria_build_permutation(_p(top_idx), _p(counts), _p(offsets), _p(dest), _p(src), T, E, k,
+                                                _stream(top_idx)), "build_permutation")
+    return offsets, dest, src
+
+
+def permute_rows(x: torch.Tensor, src_token: torch.Tensor) -> torch.Tensor:
+    _chk(x), _chk(src_token, torch.int32)
+    rows = src_token.numel()
+    out = torch.empty((rows, x.shape[1]), dtype=bf16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().aria_permute_rows(_p(x), _p(src_token), _p(out), rows, x.shape[1], _stream(x)), "permute_rows")
+    return out
+
+
+def unpermute_combine(y: torch.Tensor, dest_row: torch.Tensor, scores: torch.Tensor,
+                      shared: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(y), _chk(dest_row, torch.int32), _chk(scores)
+    T, k = scores.shape
+    out = torch.empty((T, y.shape[1]), dtype=bf16, device=y.device)
+    if shared is not None:
+        _chk(shared)
+    with torch.cuda.device(y.device):
+        L.check(L.load().aria_unpermute_combine(_p(y), _p(dest_row), _p(scores), _p(shared), _p(out), T, y.shape[1], k,
+                                                _stream(y)), "unpermute_combine")
+    return out
+
+
+def offsets_from_counts(counts: torch.Tensor) -> torch.Tensor:
+    _chk(counts, torch.int64)
+    off = torch.empty((counts.numel() + 1,), dtype=torch.int32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        L.check(L.load().aria_offsets_from_counts(_p(counts), _p(off), counts.numel(), _stream(counts)), "offsets_from_counts")
+    return off
+
+
+# ------------------------------------------------------------------------------------------- row-wise
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None):
+    """Returns norm(x) or, with residual, (norm(x + residual), x + residual)."""
+    _chk(x), _chk(weight)
+    d = x.shape[-1]
+    rows = x.numel() // d
+    out = torch.empty_like(x)
+    s = torch.empty_like(x) if residual is not None else None
+    if residual is not None:
+        _chk(residual)
+    with torch.cuda.device(x.device):
+        L.check(L.load().aria_rmsnorm(_p(x), _p(residual), _p(weight), _p(out), _p(s), rows, d, eps, _stream(x)), "rmsnorm")
+    return out if residual is None else (out, s)
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    _chk(x), _chk(weight), _chk(bias)
+    d = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.load().aria_layernorm(_p(x), _p(weight), _p(bias), _p(out), x.numel() // d, d, eps, _stream(x)), "layernorm")
+    return out
+
+
+def rope_table(inv_freq: torch.Tensor, n_pos: int):
+    _chk(inv_freq, torch.float32)
+    hd = inv_freq.numel() * 2
+    cos = torch.empty((n_pos, hd), dtype=bf16, device=inv_freq.device)
+    sin = torch.empty_like(cos)
+    with torch.cuda.device(inv_freq.device):
+        L.check(L.load().aria_rope_table(_p(inv_freq), _p(cos), _p(sin), n_pos, hd, _stream(inv_freq)), "rope_table")
+    return cos, sin
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    _chk(ids, torch.int64), _chk(table)
+    out = torch.empty((*ids.shape, table.shape[1]), dtype=bf16, device=table.device)
+    with torch.cuda.device(table.device):
+        L.check(L.load().aria_embedding(_p(ids), _p(table), _p(out), ids.numel(), table.shape[1], _stream(table)), "embedding")
+    return out
+
+
+def merge_image_features(ids: torch.Tensor, image_token: int, features: torch.Tensor, embeds: torch.Tensor,
+                         count_out: Optional[torch.Tensor] = None):
+    """In place: embeds rows at <|img|> positions <- consecutive rows of features (masked_scatter)."""
+    _chk(ids, torch.int64), _chk(features), _chk(embeds)
+    d = embeds.shape[-1]
+    with torch.cuda.device(embeds.device):
+        L.check(L.load().aria_merge_image_features(_p(ids), image_token, _p(features), _p(embeds), _p(count_out),
+                                                   ids.numel(), d, _stream(embeds)), "merge_image_features")
+    return embeds
+
+
+def im2col_patches(pixels: torch.Tensor, patch: int, k_pad: int) -> torch.Tensor:
+    _chk(pixels)
+    B, Cc, S, S2 = pixels.shape
+    assert Cc == 3 and S == S2
+    n = (S // patch) ** 2
+    out = torch.empty((B * n, k_pad), dtype=bf16, device=pixels.device)
+    with torch.cuda.device(pixels.device):
+        L.check(L.load().aria_im2col_patches(_p(pixels), _p(out), B, S, patch, k_pad, _stream(pixels)), "im2col_patches")
+    return out
+
+
+def add_pos_embedding(x: torch.Tensor, pos_ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    _chk(x), _chk(pos_ids, torch.int64), _chk(table)
+    out = torch.empty_like(x)
+    d = x.shape[-1]
+    with torch.cuda.device(x.device):
+        L.check(L.load().aria_add_pos_embedding(_p(x), _p(pos_ids), _p(table), _p(out), x.numel() // d, d, _stream(x)),
+                "add_pos_embedding")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tq: int, Tk: int, scale: float, causal: bool,
+              out_hd: int = 128, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,H,>=Tq,128], k/v [B,H,>=Tk,128] head-major (first Tq/Tk rows used) -> out [B, Tq, H*out_hd]."""
+    _chk(q), _chk(k), _chk(v)
+    B, H = q.shape[0], q.shape[1]
+    assert q.shape[-1] == 128 and k.shape[-1] == 128 and k.stride() == v.stride()
+    out = torch.empty((B, Tq, H * out_hd), dtype=bf16, device=q.device)
+    if key_mask is not None:
+        _chk(key_mask, torch.uint8)
+        assert key_mask.shape == (B, Tk)
+    with torch.cuda.device(q.device):
+        L.check(L.load().aria_attention_fwd(_p(q), _p(k), _p(v), _p(out), _p(key_mask), B, H, Tq, Tk, q.stride(0), q.stride(1),
+                                            k.stride(0), k.stride(1), out_hd, scale, int(causal), _stream(q)), "attention_fwd")
+    return out
+
+
+def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tk: int, scale: float) -> torch.Tensor:
+    """q [B,H,128] (contiguous), cache k/v [B,H,T_max,128] -> out [B, H*128]."""
+    _chk(q), _chk(k), _chk(v)
+    B, H = q.shape[0], q.shape[1]
+    lib = L.load()
+    ws_bytes = lib.aria_attention_decode_workspace_bytes(B, H, Tk)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+    out = torch.empty((B, H * 128), dtype=bf16, device=q.device)
+    with torch.cuda.device(q.device):
+        L.check(lib.aria_attention_decode(_p(q), _p(k), _p(v), _p(out), B, H, Tk, k.stride(0), k.stride(1), scale, _p(ws),
+                                          ws_bytes, _stream(q)), "attention_decode")
+    return out

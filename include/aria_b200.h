@@ -1,0 +1,170 @@
+/* aria_b200 — C ABI of the B200-native Aria hot path (libaria_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes raw DEVICE pointers + sizes + a cudaStream_t, never allocates or
+ * frees, launches asynchronously on the caller's stream and returns 0 or a negative error code.  There is
+ * no CPU fallback: unsupported shapes are errors.  Pointers must be 16-byte aligned and rows contiguous.
+ *
+ * Each function names the reference interface (rhymes-ai/Aria @ 9b25fecb) it replaces.  The reference is
+ * pure Python; its "FFI" for this path is the set of third-party kernels it imports:
+ *   grouped_gemm.ops.gmm (aria/model/moe_lm.py:432,484), flash-attn / SDPA behind the HF attention classes
+ *   (moe_lm.py:594, vision_encoder.py:120), and the ATen ops of the router / dispatcher (moe_lm.py:261-269,
+ *   329-332, 350-363).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ */
+#ifndef ARIA_B200_H
+#define ARIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* aria_stream_t; /* == cudaStream_t */
+
+#define ARIA_OK 0
+#define ARIA_ERR_BAD_ARG (-1)
+#define ARIA_ERR_UNSUPPORTED (-2)
+#define ARIA_ERR_CUDA (-3)
+
+/* Library/ABI version and build target ("sm_100a"). */
+int aria_abi_version(void);
+const char* aria_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM family (tcgen05 + TMA, bf16 in, fp32 accumulate in TMEM, bf16 out).
+ * One descriptor drives: nn.Linear-layout dense GEMMs, the reference's grouped expert GEMM, and the fused
+ * epilogues of the hot path.  Rounding points mirror the reference's op-by-op bf16 rounding.
+ * ------------------------------------------------------------------------------------------------ */
+enum { ARIA_B_NK = 0,  /* B[n_seg][N,K], K contiguous — torch.nn.Linear.weight                        */
+       ARIA_B_GKN = 1  /* B[G,K,N],      N contiguous — GroupedGEMM.weight (moe_lm.py:465)            */ };
+enum { ARIA_EPI_LINEAR = 0, /* out = act(acc + bias) (+ residual)                                      */
+       ARIA_EPI_SWIGLU = 1, /* out = silu(acc_gate) * acc_up  (moe_lm.py:505-507 `glu`, LlamaMLP)      */
+       ARIA_EPI_HEADS = 2   /* (+bias) (+RoPE) and scatter to [B, H, T, head_ld] head-major buffers    */ };
+enum { ARIA_ACT_NONE = 0, ARIA_ACT_GELU_TANH = 1, /* F.gelu(approximate="tanh") — Idefics2 MLP       */
+       ARIA_ACT_GELU_NEW = 2                       /* transformers NewGELU, op-by-op bf16 — projector  */ };
+
+typedef struct aria_gemm_desc {
+  /* A: activations [m, k] bf16, row stride lda (elements). For grouped GEMMs rows are grouped by expert. */
+  const void* a;
+  int64_t lda;
+  int64_t m, n, k;   /* n = OUTPUT columns per segment (SWIGLU: B carries 2n columns: gate then up)       */
+  /* B: weights. NK layout: up to 3 segments (e.g. q,k,v projections, or gate,up for SWIGLU), each [n,k]
+   * (SWIGLU: b[0] = gate [n,k], b[1] = up [n,k]).  GKN layout: b[0] = [G, k, n] (SWIGLU: [G, k, 2n]).  */
+  const void* b[3];
+  int32_t n_seg;
+  int32_t b_layout;
+  /* grouping: num_groups = 1 and group_offsets = NULL for a dense GEMM; else group_offsets[G+1] (device,
+   * int32) are the row offsets of each expert's contiguous row block inside A / out.                   */
+  int32_t num_groups;
+  const int32_t* group_offsets;
+  /* epilogue */
+  int32_t epilogue;
+  int32_t act;
+  const void* bias[3];     /* per segment [n] bf16 or NULL                                               */
+  const void* residual;    /* [m, n] bf16 or NULL (LINEAR only), row stride ldr                          */
+  int64_t ldr;
+  void* out[3];            /* LINEAR/SWIGLU: out[0] = [m, n_seg*n] row stride ldo; HEADS: one per segment */
+  int64_t ldo;
+  /* HEADS epilogue: row r of A is (batch r / rows_per_batch, token r % rows_per_batch); column c of
+   * segment s is (head c / head_dim, d c % head_dim); destination element
+   *   out[s] + batch*stride_b + head*stride_h + (pos0 + token)*head_ld + d                              */
+  int32_t head_dim, head_ld, rows_per_batch, pos0;
+  int64_t stride_b, stride_h;
+  int32_t rope_mask;       /* bit s set: apply rotate-half RoPE to segment s (needs head_dim == 128)     */
+  const void* rope_cos;    /* [max_pos, head_dim] bf16 tables (aria_rope_table)                          */
+  const void* rope_sin;
+  const int32_t* position_ids; /* [m] or NULL (then position = pos0 + token)                              */
+  /* debug overrides of the UMMA shared-memory descriptor fields (0 = default); bring-up only            */
+  int32_t dbg_lbo, dbg_sbo, dbg_kadv;
+} aria_gemm_desc_t;
+
+/* Generic entry.  Replaces: torch F.linear / cuBLAS on the path, and grouped_gemm.ops.gmm. */
+int aria_gemm(const aria_gemm_desc_t* desc, aria_stream_t stream);
+
+/* Drop-in for `grouped_gemm.ops.gmm(a, b, batch_sizes)` as called at moe_lm.py:484 (`experts_gemm`), except
+ * that the per-expert row offsets stay on the device (no .cpu() sync, moe_lm.py:478):
+ *   out[off[e]:off[e+1]] = a[off[e]:off[e+1]] @ b[e],  a [rows,k], b [G,k,n], out [rows,n], all bf16.      */
+int aria_grouped_gemm(const void* a, const void* b, void* out, const int32_t* group_offsets, int64_t rows,
+                      int64_t k, int64_t n, int32_t num_groups, aria_stream_t stream);
+
+/* int64 counts (tokens_per_expert as the reference passes it, moe_lm.py:264-269) -> int32 offsets[G+1]. */
+int aria_offsets_from_counts(const int64_t* counts, int32_t* offsets, int32_t num_groups, aria_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MoE routing / dispatch (HBM-bound kernels)
+ * ------------------------------------------------------------------------------------------------ */
+/* TopKRouter.forward (moe_lm.py:275-293 = gating :190-201 + routing :261-269), eval path.
+ *   x [T, d] bf16, w_router [E, d] bf16 -> logits [T, E] bf16 (optional, may be NULL),
+ *   top_idx [T, k] int32 (descending logit, ties: lowest expert id), scores [T, k] bf16 (fp32 softmax over
+ *   the k selected bf16 logits, rounded to bf16), counts [E] int32 (must be zeroed by this call: it is).
+ * E <= 64, k <= 8. */
+int aria_router_topk(const void* x, const void* w_router, void* logits_out, int32_t* top_idx, void* scores,
+                     int32_t* counts, int64_t T, int32_t d, int32_t E, int32_t k, aria_stream_t stream);
+/* Same routing from precomputed bf16 logits (exact integer/bit parity path; torch.topk + softmax + histc). */
+int aria_route_from_logits(const void* logits, int32_t* top_idx, void* scores, int32_t* counts, int64_t T,
+                           int32_t E, int32_t k, aria_stream_t stream);
+
+/* TokenDispatcher.token_permutation (moe_lm.py:313-334): stable counting sort of the T*k expert ids.
+ *   offsets [E+1] int32 (exclusive scan of counts), dest_row [T*k] int32 (row of flattened (token,slot) in
+ *   the expert-sorted order == inverse of the reference's `sorted_indices`), src_token [T*k] int32 (token of
+ *   each sorted row == sorted_indices // k).  Order inside an expert = ascending flattened index (stable). */
+int aria_build_permutation(const int32_t* top_idx, const int32_t* counts, int32_t* offsets, int32_t* dest_row,
+                           int32_t* src_token, int64_t T, int32_t E, int32_t k, aria_stream_t stream);
+/*   permuted[r, :] = x[src_token[r], :]  (index_select, moe_lm.py:330) */
+int aria_permute_rows(const void* x, const int32_t* src_token, void* permuted, int64_t rows, int32_t d,
+                      aria_stream_t stream);
+/* TokenDispatcher.token_unpermutation (moe_lm.py:336-365) fused with `output += shared` (moe_lm.py:576):
+ *   out[t] = bf16( sum_j bf16(y[dest_row[t*k+j]] * scores[t,j]) ) (+ shared[t]) ; fp32 accumulate. */
+int aria_unpermute_combine(const void* y, const int32_t* dest_row, const void* scores, const void* shared,
+                           void* out, int64_t T, int32_t d, int32_t k, aria_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Norms, RoPE table, embedding, patches
+ * ------------------------------------------------------------------------------------------------ */
+/* LlamaRMSNorm (moe_lm.py:599-602,631): out = w * bf16(x * rsqrt(mean(x^2) + eps)).
+ * If residual != NULL: first h = bf16(x + residual), written to sum_out, and the norm is taken of h. */
+int aria_rmsnorm(const void* x, const void* residual, const void* weight, void* out, void* sum_out, int64_t rows,
+                 int32_t d, float eps, aria_stream_t stream);
+/* nn.LayerNorm (Idefics2 encoder layers, projector): out = bf16((x-mean)*rstd*w + b). */
+int aria_layernorm(const void* x, const void* weight, const void* bias, void* out, int64_t rows, int32_t d,
+                   float eps, aria_stream_t stream);
+/* LlamaRotaryEmbedding (moe_lm.py:632): cos/sin [n_pos, head_dim] bf16 from fp32 inv_freq[head_dim/2]. */
+int aria_rope_table(const float* inv_freq, void* cos_out, void* sin_out, int32_t n_pos, int32_t head_dim,
+                    aria_stream_t stream);
+/* nn.Embedding gather: out[i] = table[ids[i]]. */
+int aria_embedding(const int64_t* ids, const void* table, void* out, int64_t n, int32_t d, aria_stream_t stream);
+/* masked_scatter merge (modeling_aria.py:272-283): rows where ids == image_token get consecutive rows of
+ * `features`; `slot_index` [n] int32 scratch.  Returns the number of image slots through *count_out (device). */
+int aria_merge_image_features(const int64_t* ids, int64_t image_token, const void* features, void* embeds,
+                              int32_t* count_out, int64_t n, int32_t d, aria_stream_t stream);
+/* Conv2d(3,C,14,14) as im2col: pixel_values [B,3,S,S] bf16 -> patches [B*N, k_pad] (k = 3*P*P zero padded). */
+int aria_im2col_patches(const void* pixels, void* patches, int32_t B, int32_t S, int32_t P, int32_t k_pad,
+                        aria_stream_t stream);
+/* out[r,:] = bf16(x[r,:] + table[pos[r],:]) — position-embedding add of Idefics2VisionEmbeddings. */
+int aria_add_pos_embedding(const void* x, const int64_t* pos_ids, const void* table, void* out, int64_t rows,
+                           int32_t d, aria_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (tcgen05 QK^T / PV, fp32 online softmax)
+ * ------------------------------------------------------------------------------------------------ */
+/* softmax(q k^T * scale + mask) v for head_dim 128 (LM) — replaces flash_attn_func / SDPA behind
+ * LLAMA_ATTENTION_CLASSES (moe_lm.py:594) and, with hd padded 72->128, the Idefics2 / projector attention.
+ *   q [B, H, Tq, 128], k/v [B, H, Tk_max, 128] head-major bf16 (HF cache layout), first Tk rows valid.
+ *   out [B, Tq, H*out_hd] token-major bf16 (only the first out_hd of 128 dims are written).
+ *   causal != 0: query i (absolute position Tk - Tq + i) sees keys <= its position.
+ *   key_mask [B, Tk] uint8 or NULL: 1 = key is masked OUT (image_attn_mask convention, vision_encoder.py:147). */
+int aria_attention_fwd(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask,
+                       int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t q_stride_b, int64_t q_stride_h,
+                       int64_t kv_stride_b, int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal,
+                       aria_stream_t stream);
+/* Single-token decode against a KV cache (HBM-bound, split-KV): q [B,H,128], cache [B,H,Tk_max,128].
+ * workspace: B*H*splits*(128+2) floats. */
+int aria_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tk,
+                          int64_t kv_stride_b, int64_t kv_stride_h, float scale, void* workspace,
+                          int64_t workspace_bytes, aria_stream_t stream);
+int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, int32_t Tk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARIA_B200_H */
