@@ -85,6 +85,13 @@ def load():
     return lib
 
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches`; memsets are not counted)
+KERNELS_PER_CALL = {"router_topk": 2, "attention_decode": 2}
+launch_count = 0
+
+
 def check(rc: int, what: str):
+    global launch_count
     if rc != ARIA_OK:
         raise RuntimeError(f"aria_b200: {what} failed: {_ERR.get(rc, rc)}")
+    launch_count += KERNELS_PER_CALL.get(what, 1)

@@ -1,0 +1,131 @@
+"""Host-side mirror of `aria/model/modeling_aria.py`: AriaForConditionalGeneration.forward()/generate() with the
+Hugging Face state-dict layout, running entirely on the B200-native kernels.
+
+forward() follows modeling_aria.py:194-335: embed -> vision tower -> projector -> masked_scatter merge -> LM.
+Differences that are deliberate: no autograd / labels path (inference hot path only), the KV cache is our
+static `KVCache` (HF layout [B,H,T,hd] per layer), integer index tensors stay int32 on the device.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .moe_lm import AriaMoELMConfig, AriaMoELMForCausalLM, KVCache, bf16
+from .projector import AriaProjector
+from .vision_encoder import AriaVisionConfig, AriaVisionModel
+
+
+class AriaConfig:
+    """configuration_aria.py:31-114 (attributes used on the hot path)."""
+
+    def __init__(self, vision_config, text_config, projector_patch_to_query_dict=None, image_token_index=32000,
+                 ignore_index=-100, **_ignored):
+        self.vision_config = vision_config if not isinstance(vision_config, dict) else AriaVisionConfig(**vision_config)
+        self.text_config = text_config if not isinstance(text_config, dict) else AriaMoELMConfig(**text_config)
+        self.projector_patch_to_query_dict = {int(k): int(v) for k, v in
+                                              (projector_patch_to_query_dict or {1225: 128, 4900: 256}).items()}
+        self.image_token_index = image_token_index
+        self.ignore_index = ignore_index
+
+    @classmethod
+    def from_dict(cls, cfg: dict):
+        """From the plain-dict configs used by oracle/configs.py and bench.py."""
+        return cls(cfg["vision_config"], cfg["text_config"], cfg["projector"]["patch_to_query_dict"],
+                   cfg["image_token_index"])
+
+
+class AriaCausalLMOutputWithPast:
+    def __init__(self, logits, past_key_values):
+        self.logits = logits
+        self.past_key_values = past_key_values
+        self.loss = None
+
+
+class AriaForConditionalGeneration(nn.Module):
+    """modeling_aria.py:125-365."""
+
+    def __init__(self, config: AriaConfig, device=None):
+        super().__init__()
+        self.config = config
+        v, t = config.vision_config, config.text_config
+        self.vision_tower = AriaVisionModel(v, device)
+        self.multi_modal_projector = AriaProjector(  # build_mm_projector, modeling_aria.py:102-122
+            config.projector_patch_to_query_dict, v.hidden_size, v.num_attention_heads, v.hidden_size, t.hidden_size,
+            t.hidden_size, device)
+        self.vocab_size = t.vocab_size
+        self.language_model = AriaMoELMForCausalLM(t, device)
+
+    def get_input_embeddings(self):
+        return self.language_model.model.embed_tokens
+
+    @property
+    def device(self):
+        return self.language_model.lm_head.weight.device
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor = None, pixel_values: Optional[torch.Tensor] = None,
+                pixel_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
+                inputs_embeds: Optional[torch.Tensor] = None, num_logits_to_keep: int = 0,
+                max_cache_len: Optional[int] = None, input_ids_host: Optional[torch.Tensor] = None,
+                **_unused) -> AriaCausalLMOutputWithPast:
+        """input_ids / pixel_values / pixel_mask may be HOST tensors (pinned for async copies): they are copied to
+        the device on the current stream; image-token bookkeeping is then done on the host copy (no device sync).
+        Device-resident input_ids cost one sync for the image-token count check, like the reference's `.item()`
+        (modeling_aria.py:265)."""
+        dev = self.device
+        ids_host = input_ids_host  # optional host copy of device-resident ids (bookkeeping without a sync)
+        if input_ids is not None and not input_ids.is_cuda:
+            ids_host = input_ids
+            input_ids = input_ids.to(dev, non_blocking=True)
+        if pixel_values is not None and not pixel_values.is_cuda:
+            pixel_values = pixel_values.to(dev, non_blocking=True)
+        if inputs_embeds is None:
+            inputs_embeds = ops.embedding(input_ids.contiguous(), self.get_input_embeddings().weight)
+
+        if pixel_values is not None:
+            feats, image_attn_mask = self.vision_tower(pixel_values.to(bf16), pixel_mask)
+            image_features = self.multi_modal_projector(feats, image_attn_mask)
+            n_image_features = image_features.shape[0] * image_features.shape[1]
+            src = ids_host if ids_host is not None else input_ids
+            n_image_tokens = int((src == self.config.image_token_index).sum())
+            if n_image_tokens != n_image_features:
+                raise ValueError(  # modeling_aria.py:268-271
+                    f"Image features and image tokens do not match: tokens: {n_image_tokens}, features {n_image_features}")
+            ops.merge_image_features(input_ids.reshape(-1).contiguous(), self.config.image_token_index,
+                                     image_features.reshape(-1, image_features.shape[-1]),
+                                     inputs_embeds.view(-1, inputs_embeds.shape[-1]))
+
+        B, T, _ = inputs_embeds.shape
+        cache = past_key_values
+        if cache is None:
+            cache = self.language_model.new_cache(B, max_cache_len or T, dev)
+        logits, cache = self.language_model(inputs_embeds, cache, num_logits_to_keep)
+        return AriaCausalLMOutputWithPast(logits, cache)
+
+    @torch.no_grad()
+    def generate(self, input_ids, pixel_values=None, pixel_mask=None, max_new_tokens: int = 16):
+        """Greedy decoding (the reference goes through HF GenerationMixin, modeling_aria.py:125,337-365):
+        prefill with the image, then one token per step against the KV cache (pixel inputs only at step 0)."""
+        B, T = input_ids.shape
+        out = self.forward(input_ids, pixel_values, pixel_mask, num_logits_to_keep=1, max_cache_len=T + max_new_tokens)
+        cache = out.past_key_values
+        tokens = [out.logits[:, -1].float().argmax(-1)]
+        for _ in range(max_new_tokens - 1):
+            step = self.forward(tokens[-1].view(B, 1), past_key_values=cache, num_logits_to_keep=1)
+            tokens.append(step.logits[:, -1].float().argmax(-1))
+        return torch.cat([input_ids.to(tokens[0].device), torch.stack(tokens, 1)], dim=1)
+
+
+def init_random_(model: nn.Module, seed: int = 0, std: float = 0.02):
+    """Random-init (no checkpoint offline): N(0, std^2) for matrices / embeddings / biases / queries, 1 for the
+    norm scales (the only 1-D parameters named `weight`)."""
+    g = torch.Generator(device=next(model.parameters()).device).manual_seed(seed)
+    for name, p in model.named_parameters():
+        if p.dim() == 1 and name.endswith("weight"):
+            p.fill_(1.0)
+        else:
+            p.normal_(0.0, std, generator=g)
+    return model

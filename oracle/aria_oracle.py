@@ -203,7 +203,7 @@ def lm_attention(x: Tensor, w: Dict[str, Tensor], prefix: str, n_heads: int, the
 
 
 def moe_decoder_layer(x: Tensor, w: Dict[str, Tensor], prefix: str, cfg, position_ids: Tensor,
-                      past_kv=None):
+                      past_kv=None, router_logits: Optional[list] = None):
     """LlamaDecoderLayer.forward with mlp=MoELayer (moe_lm.py:590-602)."""
     r = x
     h = rms_norm(x, w[prefix + "input_layernorm.weight"], cfg["rms_norm_eps"])
@@ -212,12 +212,16 @@ def moe_decoder_layer(x: Tensor, w: Dict[str, Tensor], prefix: str, cfg, positio
     x = r + h
     r = x
     h = rms_norm(x, w[prefix + "post_attention_layernorm.weight"], cfg["rms_norm_eps"])
-    h = moe_layer(h, w, cfg["moe_topk"], prefix + "mlp.")
+    if router_logits is not None:
+        h, parts = moe_layer(h, w, cfg["moe_topk"], prefix + "mlp.", return_parts=True)
+        router_logits.append(parts["logits"])
+    else:
+        h = moe_layer(h, w, cfg["moe_topk"], prefix + "mlp.")
     return r + h, kv
 
 
 def lm_forward(inputs_embeds: Tensor, w: Dict[str, Tensor], cfg, prefix: str = "language_model.",
-               past=None, num_logits_to_keep: int = 0):
+               past=None, num_logits_to_keep: int = 0, router_logits: Optional[list] = None):
     """AriaMoELMForCausalLM.forward (moe_lm.py:605-661): layers -> final RMSNorm -> lm_head."""
     B, T, _ = inputs_embeds.shape
     past_len = 0 if past is None else past[0][0].shape[2]
@@ -226,7 +230,7 @@ def lm_forward(inputs_embeds: Tensor, w: Dict[str, Tensor], cfg, prefix: str = "
     new_past = []
     for i in range(cfg["num_hidden_layers"]):
         x, kv = moe_decoder_layer(x, w, f"{prefix}model.layers.{i}.", cfg, position_ids,
-                                  None if past is None else past[i])
+                                  None if past is None else past[i], router_logits)
         new_past.append(kv)
     x = rms_norm(x, w[prefix + "model.norm.weight"], cfg["rms_norm_eps"])
     if num_logits_to_keep:
@@ -262,6 +266,41 @@ def vit_position_ids(pmask: Tensor, n_side: int, dtype) -> Tensor:
     return pos
 
 
+def vit_embeddings(pixel_values: Tensor, pmask: Tensor, w: Dict[str, Tensor], vcfg, prefix: str) -> Tensor:
+    """Idefics2VisionEmbeddings.forward: Conv2d patch embedding + bucketised position embedding."""
+    P = vcfg["patch_size"]
+    x = F.conv2d(pixel_values, w[prefix + "embeddings.patch_embedding.weight"],
+                 w[prefix + "embeddings.patch_embedding.bias"], stride=P)
+    x = x.flatten(2).transpose(1, 2)
+    pos = vit_position_ids(pmask, vcfg["image_size"] // P, pixel_values.dtype)
+    return x + F.embedding(pos, w[prefix + "embeddings.position_embedding.weight"])
+
+
+def vit_encoder_layer(x: Tensor, w: Dict[str, Tensor], p: str, vcfg, add_mask: Optional[Tensor]) -> Tensor:
+    """Idefics2EncoderLayer.forward: pre-LN MHA (bias, non-causal, key mask) + pre-LN MLP (gelu_pytorch_tanh)."""
+    B, N, d = x.shape
+    H = vcfg["num_attention_heads"]
+    hd = d // H
+    eps = vcfg["layer_norm_eps"]
+    r = x
+    h = F.layer_norm(x, (d,), w[p + "layer_norm1.weight"], w[p + "layer_norm1.bias"], eps)
+    q = F.linear(h, w[p + "self_attn.q_proj.weight"], w[p + "self_attn.q_proj.bias"])
+    k = F.linear(h, w[p + "self_attn.k_proj.weight"], w[p + "self_attn.k_proj.bias"])
+    v = F.linear(h, w[p + "self_attn.v_proj.weight"], w[p + "self_attn.v_proj.bias"])
+    q = q.view(B, N, H, hd).transpose(1, 2)
+    k = k.view(B, N, H, hd).transpose(1, 2)
+    v = v.view(B, N, H, hd).transpose(1, 2)
+    o = attention_core(q, k, v, hd ** -0.5, add_mask).reshape(B, N, d)
+    o = F.linear(o, w[p + "self_attn.out_proj.weight"], w[p + "self_attn.out_proj.bias"])
+    x = r + o
+    r = x
+    h = F.layer_norm(x, (d,), w[p + "layer_norm2.weight"], w[p + "layer_norm2.bias"], eps)
+    h = F.linear(h, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])
+    h = F.gelu(h, approximate="tanh")  # gelu_pytorch_tanh
+    h = F.linear(h, w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
+    return r + h
+
+
 def vit_forward(pixel_values: Tensor, pixel_mask: Optional[Tensor], w: Dict[str, Tensor], vcfg,
                 prefix: str = "vision_tower.vision_model."):
     """AriaVisionModel.forward (vision_encoder.py:94-130) over AriaVisionTransformer (:58-67: no
@@ -273,40 +312,14 @@ def vit_forward(pixel_values: Tensor, pixel_mask: Optional[Tensor], w: Dict[str,
         pmask = torch.ones(B, pixel_values.shape[2] // P, pixel_values.shape[3] // P, dtype=torch.bool)
     else:
         pmask = patch_attention_mask(pixel_mask, P)
-    x = F.conv2d(pixel_values, w[prefix + "embeddings.patch_embedding.weight"],
-                 w[prefix + "embeddings.patch_embedding.bias"], stride=P)
-    x = x.flatten(2).transpose(1, 2)
-    pos = vit_position_ids(pmask, vcfg["image_size"] // P, dt)
-    x = x + F.embedding(pos, w[prefix + "embeddings.position_embedding.weight"])
+    x = vit_embeddings(pixel_values, pmask, w, vcfg, prefix)
     flat = pmask.view(B, -1)
     add_mask = None
     if not bool(flat.all()):
         add_mask = torch.zeros(B, 1, 1, flat.shape[1], dtype=dt)
         add_mask.masked_fill_(~flat[:, None, None, :], torch.finfo(dt).min)
-    H = vcfg["num_attention_heads"]
-    d = x.shape[-1]
-    hd = d // H
-    eps = vcfg["layer_norm_eps"]
-    N = x.shape[1]
     for i in range(vcfg["num_hidden_layers"]):
-        p = f"{prefix}encoder.layers.{i}."
-        r = x
-        h = F.layer_norm(x, (d,), w[p + "layer_norm1.weight"], w[p + "layer_norm1.bias"], eps)
-        q = F.linear(h, w[p + "self_attn.q_proj.weight"], w[p + "self_attn.q_proj.bias"])
-        k = F.linear(h, w[p + "self_attn.k_proj.weight"], w[p + "self_attn.k_proj.bias"])
-        v = F.linear(h, w[p + "self_attn.v_proj.weight"], w[p + "self_attn.v_proj.bias"])
-        q = q.view(B, N, H, hd).transpose(1, 2)
-        k = k.view(B, N, H, hd).transpose(1, 2)
-        v = v.view(B, N, H, hd).transpose(1, 2)
-        o = attention_core(q, k, v, hd ** -0.5, add_mask).reshape(B, N, d)
-        o = F.linear(o, w[p + "self_attn.out_proj.weight"], w[p + "self_attn.out_proj.bias"])
-        x = r + o
-        r = x
-        h = F.layer_norm(x, (d,), w[p + "layer_norm2.weight"], w[p + "layer_norm2.bias"], eps)
-        h = F.linear(h, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])
-        h = F.gelu(h, approximate="tanh")  # gelu_pytorch_tanh
-        h = F.linear(h, w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
-        x = r + h
+        x = vit_encoder_layer(x, w, f"{prefix}encoder.layers.{i}.", vcfg, add_mask)
     return x, torch.logical_not(flat)  # vision_encoder.py:147-152
 
 
@@ -356,8 +369,20 @@ def projector_forward(x: Tensor, image_attn_mask: Optional[Tensor], w: Dict[str,
 # ----------------------------------------------------------------------------------------------
 # Full model  (aria/model/modeling_aria.py:194-335)
 # ----------------------------------------------------------------------------------------------
+def topk_margin(router_logits: list, k: int) -> Tensor:
+    """Per token: the smallest gap, over all layers, between the k-th and (k+1)-th router logit relative to the
+    largest |logit|.  Tokens whose margin is within bf16 rounding noise may legitimately be routed to another
+    expert by an implementation with a different fp32 summation order; parity tests treat them separately."""
+    m = None
+    for lg in router_logits:
+        v = lg.float().sort(dim=1, descending=True).values
+        gap = (v[:, k - 1] - v[:, k]) / v.abs().amax(dim=1).clamp_min(1e-12)
+        m = gap if m is None else torch.minimum(m, gap)
+    return m
+
+
 def aria_forward(input_ids: Tensor, pixel_values: Optional[Tensor], pixel_mask: Optional[Tensor],
-                 w: Dict[str, Tensor], cfg, num_logits_to_keep: int = 0):
+                 w: Dict[str, Tensor], cfg, num_logits_to_keep: int = 0, router_logits: Optional[list] = None):
     """AriaForConditionalGeneration.forward: embed -> ViT -> projector -> masked_scatter merge -> LM."""
     tcfg = cfg["text_config"]
     emb = F.embedding(input_ids, w["language_model.model.embed_tokens.weight"])
@@ -371,5 +396,5 @@ def aria_forward(input_ids: Tensor, pixel_values: Optional[Tensor], pixel_mask: 
                 f"features {feats.shape[0] * feats.shape[1]}")
         m = (input_ids == cfg["image_token_index"]).unsqueeze(-1).expand_as(emb)
         emb = emb.masked_scatter(m, feats.to(emb.dtype))
-    logits, past = lm_forward(emb, w, tcfg, num_logits_to_keep=num_logits_to_keep)
+    logits, past = lm_forward(emb, w, tcfg, num_logits_to_keep=num_logits_to_keep, router_logits=router_logits)
     return logits, past

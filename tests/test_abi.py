@@ -1,0 +1,103 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/aria_b200.h declares; the ctypes
+mirror of the descriptor struct matches the header field for field.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "aria_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aria_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from aria_b200 import build, _lib
+    build.build()  # nvcc cross-compiles sm_100a without a GPU
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from aria_b200 import _lib
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/aria_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in aria_b200/_lib.py"
+
+
+def test_version_and_arch(lib):
+    assert lib.aria_abi_version() == 1
+    assert lib.aria_build_arch() == b"sm_100a"
+
+
+def test_gemm_desc_matches_header():
+    from aria_b200 import _lib
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct aria_gemm_desc {"):src.index("} aria_gemm_desc_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(void|int64_t|int32_t)\s*\*?", "", decl).strip()
+        for part in decl.split(","):
+            names.append(re.sub(r"[\*\s]|\[\d+\]", "", part))
+    assert names == [f[0] for f in _lib.GemmDesc._fields_]
+    # 8-byte pointers / int64, natural alignment
+    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+
+
+def test_bad_arguments_are_errors_not_crashes(lib):
+    """Argument validation happens before any CUDA call, so it is testable without a GPU."""
+    from aria_b200 import _lib
+    d = _lib.GemmDesc()
+    assert lib.aria_gemm(ctypes.byref(d), None) == -1  # null pointers
+    assert lib.aria_route_from_logits(None, None, None, None, 4, 8, 2, None) == -1
+    assert lib.aria_permute_rows(None, None, None, 4, 256, None) == -1
+    assert lib.aria_attention_decode_workspace_bytes(32, 20, 2048) == 32 * 20 * 8 * 130 * 4
+
+
+def test_no_cpu_fallback():
+    """ops refuse CPU tensors loudly."""
+    import torch
+    from aria_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "aria_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src.replace("oracle/configs.py", "").replace("oracle/aria_oracle.py", ""), f
+
+
+def test_state_dict_keys_match_hf_layout():
+    import torch
+    from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration
+    from oracle import configs as C
+    m = AriaForConditionalGeneration(AriaConfig.from_dict(C.TINY), device="cpu")
+    sd = C.aria_state(C.TINY, seed=0, dtype=torch.bfloat16)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    # reference GroupedGEMM layout: [E, in, out] (moe_lm.py:465)
+    w = m.language_model.model.layers[0].mlp.experts.fc1.weight
+    assert tuple(w.shape) == (8, 256, 1024)
+
+
+def test_offsets_contract():
+    import torch
+    from aria_b200 import moe_lm
+    with pytest.raises(RuntimeError):
+        moe_lm._as_offsets(torch.zeros(5, dtype=torch.int64), 8, "cpu")  # neither E nor E+1 entries
+    with pytest.raises(RuntimeError):
+        moe_lm._as_offsets(torch.zeros(9, dtype=torch.int64), 8, "cpu")  # offsets must be int32 CUDA
