@@ -2,16 +2,19 @@
 //
 // aria_attention_fwd: flash-style forward with both contractions on tcgen05 tensor cores:
 //     S = Q K^T   (A = Q tile, B = K tile, both K-major SW128 in shared memory, accumulator S in TMEM)
-//     O += P V    (A = P tile written by the softmax warps into SW128 shared memory, B = V tile consumed
-//                  MN-major — V is [keys, d] with d contiguous, exactly the HF cache layout — O in TMEM)
+//     O += P V    (A = P, bf16, written by the softmax warps back into TMEM over S and consumed straight from
+//                  TMEM; B = V tile consumed MN-major — V is [keys, d] with d contiguous, exactly the HF cache
+//                  layout — O accumulates in TMEM)
 //   warp 0: TMA producer (Q once, K/V double buffered); warp 1: MMA issuer + TMEM owner;
-//   warps 2-5: softmax (one query row per thread: tcgen05.ld of S, fp32 online softmax with warp-uniform
-//   lazy rescale of O, P -> shared memory) and the final normalise + store.
+//   warps 2-9: softmax (one query row per thread, whole S row in registers, fp32 online softmax with a
+//   warp-uniform lazy rescale of O) and the final normalise + store.
 // Replaces flash_attn_func / SDPA behind LLAMA_ATTENTION_CLASSES (aria/model/moe_lm.py:594) and the
 // Idefics2 / nn.MultiheadAttention attention of the ViT + projector (vision_encoder.py:120,
 // projector.py:93) with head_dim padded 72 -> 128.
 //
 // aria_attention_decode: single-query attention against the KV cache; HBM-bound, CUDA cores, split-KV.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -22,8 +25,13 @@ constexpr int AT_BN = 128;   // keys per step
 constexpr int AT_D = 128;    // head dim
 constexpr int AT_TILE = AT_BM * AT_D * 2;  // 32 KB
 constexpr int AT_HALF = AT_TILE / 2;       // one SW128 atom column: [128 rows][64 bf16]
-constexpr int AT_THREADS = 192;
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + AT_TILE /*P*/ + 1024 + 256;
+
+// ex2.approx: one MUFU op, no range-handling branches (inputs here are <= 8 and finite or -inf)
+ARIA_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnParams {
   int B, H, Tq, Tk;
@@ -35,39 +43,48 @@ struct AttnParams {
   int n_q_tiles;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+// ------------------------------------------------------------------------------------------------
+// Two 128-row query tiles per CTA (256 queries) ping-pong on the tensor core (FA4-style):
+//   TMEM: S0 | S1 | O0 | O1 (4 x 128 columns).  P_t (bf16) aliases the first 64 columns of S_t and is fed to the
+//   PV MMA straight from TMEM (tcgen05.mma A-from-TMEM), so P never touches shared memory.
+//   warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax of tile 0, warps 6-9 softmax of tile 1.
+//   MMA issue order per key block j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  — tile 1's softmax runs under tile 0's MMAs
+//   and vice versa; tcgen05 ops execute in issue order, which is what makes the S/P aliasing safe.
+constexpr int A2_THREADS = 320;
+constexpr int A2_SMEM = 2 * AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_TILE;
-  uint8_t* sV = sK + 2 * AT_TILE;
-  uint8_t* sP = sV + 2 * AT_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_TILE);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint8_t* sQ = smem;                 // [2 tiles][32 KB]
+  uint8_t* sK = sQ + 2 * AT_TILE;     // [2 stages][32 KB]
+  uint8_t* sV = sK + 2 * AT_TILE;     // [2 stages][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * AT_TILE);
+  uint64_t* q_full = bars;         // [1]
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [2]
+  uint64_t* kv_empty = bars + 5;   // [2]
+  uint64_t* s_full = bars + 7;     // [2] per tile
+  uint64_t* p_full = bars + 9;     // [2] per tile
+  uint64_t* o_full = bars + 11;    // [2] per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // heavy (late) causal query tiles first
   const int bh = blockIdx.x % (p.B * p.H);
-  const int q_tile = p.n_q_tiles - 1 - blockIdx.x / (p.B * p.H);
+  const int q_pair = p.n_q_tiles - 1 - blockIdx.x / (p.B * p.H);  // n_q_tiles = number of 256-row pairs here
   const int b = bh / p.H, h = bh % p.H;
-  const int q0 = q_tile * AT_BM;
-  const int pos_off = p.Tk - p.Tq;  // absolute position of query 0
-  int n_kv = (p.Tk + AT_BN - 1) / AT_BN;
+  const int q0 = q_pair * 2 * AT_BM;
+  const int pos_off = p.Tk - p.Tq;
+  const bool act1 = q0 + AT_BM < p.Tq;  // second tile has at least one valid row
+  const int n_kv_all = (p.Tk + AT_BN - 1) / AT_BN;
+  int n_kv0 = n_kv_all, n_kv1 = act1 ? n_kv_all : 0;
   if (p.causal) {
-    int last = pos_off + min(q0 + AT_BM, p.Tq) - 1;  // last visible key of this tile
-    int lim = last / AT_BN + 1;
-    if (lim < n_kv) n_kv = lim;
+    n_kv0 = min(n_kv_all, (pos_off + min(q0 + AT_BM, p.Tq) - 1) / AT_BN + 1);
+    if (act1) n_kv1 = min(n_kv_all, (pos_off + min(q0 + 2 * AT_BM, p.Tq) - 1) / AT_BN + 1);
   }
+  const int n_kv = max(n_kv0, n_kv1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
@@ -78,28 +95,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // columns [0,128)
-  const uint32_t tO = tmem_base + 128;  // columns [128,256)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE);
+      mbar_arrive_expect_tx(q_full, act1 ? 2 * AT_TILE : AT_TILE);
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
       tma_load_4d(sQ + AT_HALF, &tmQ, q_full, 64, q0, h, b);
+      if (act1) {
+        tma_load_4d(sQ + AT_TILE, &tmQ, q_full, 0, q0 + AT_BM, h, b);
+        tma_load_4d(sQ + AT_TILE + AT_HALF, &tmQ, q_full, 64, q0 + AT_BM, h, b);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
@@ -115,156 +134,163 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(AT_BM, AT_D, false, true);
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sK + s * AT_TILE);
+      auto issue_qk = [&](int t, int j) {
+        const uint32_t aQ = smem_u32(sQ + t * AT_TILE);
+        const uint32_t aK = smem_u32(sK + (j & 1) * AT_TILE);
+        const uint32_t tS = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k) {
           const uint32_t off = (k >> 2) * AT_HALF + (k & 3) * 32;
           umma_bf16_ss(tS, make_smem_desc(aQ + off, 16, 1024), make_smem_desc(aK + off, 16, 1024), idesc_qk, k ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {
+        const uint32_t aV = smem_u32(sV + (j & 1) * AT_TILE);
+        const uint32_t tP = tmem_base + t * 128;        // bf16 P aliases S_t (2 elements per 32-bit column)
+        const uint32_t tO = tmem_base + 256 + t * 128;
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k)
+          umma_bf16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, AT_HALF, 1024), idesc_pv, (j | k) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (act1) issue_qk(1, 0);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         mbar_wait(&v_full[s], (j >> 1) & 1);
-        mbar_wait(p_full, j & 1);  // P(j) in smem, O rescaled, S(j) consumed
-        tc_fence_after();
-        const uint32_t aV = smem_u32(sV + s * AT_TILE);
-#pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k) {
-          // A = P: K-major, keys k*16.. -> atom (k>>2), +32 B per step; B = V: MN-major, 16 key rows = 2048 B
-          const uint64_t da = make_smem_desc(aP + (k >> 2) * AT_HALF + (k & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(aV + k * 2048, AT_HALF, 1024);
-          umma_bf16_ss(tO, da, db, idesc_pv, (j | k) ? 1u : 0u);
+        bool k_next_ready = false;
+        if (j < n_kv0) {
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(0, j);
+          if (j == n_kv0 - 1) umma_commit(&o_full[0]);
+          if (j + 1 < n_kv0) {
+            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            k_next_ready = true;
+            tc_fence_after();
+            issue_qk(0, j + 1);
+          }
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(o_full);
-        if (j + 1 < n_kv) issue_qk(j + 1);
+        if (j < n_kv1) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, j);
+          if (j == n_kv1 - 1) umma_commit(&o_full[1]);
+          if (j + 1 < n_kv1) {
+            if (!k_next_ready) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_qk(1, j + 1);
+          }
+        }
+        umma_commit(&kv_empty[s]);  // everything that read K(j)/V(j) has been issued before this point
       }
     }
   } else {
-    // ------------------------------ softmax / correction / epilogue: one query row per thread
+    const int t = (warp - 2) >> 2;  // query tile of this softmax warpgroup
+    const int n_kv_t = t == 0 ? n_kv0 : n_kv1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int q = q0 + r;
+    const int q = q0 + t * AT_BM + r;
     const bool row_ok = q < p.Tq;
     const int qpos = pos_off + q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_addr;
+    const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
     const uint8_t* km = p.key_mask ? p.key_mask + static_cast<int64_t>(b) * p.Tk : nullptr;
     float m_ref = -INFINITY, l = 0.f;
-    uint8_t* prow = sP + r * 128;
 
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+    for (int j = 0; j < n_kv_t; ++j) {
+      mbar_wait(&s_full[t], j & 1);  // also implies PV_t(j-1) completed (commit covers all earlier MMAs)
       tc_fence_after();
       const int k0 = j * AT_BN;
-      const bool need_mask = (k0 + AT_BN > p.Tk) || (p.causal && (k0 + AT_BN - 1 > pos_off + q0)) || km != nullptr;
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c, v);
-        tmem_ld_wait();
+      const bool need_mask = (k0 + AT_BN > p.Tk) || (p.causal && (k0 + AT_BN - 1 > pos_off + q0 + t * AT_BM)) || km != nullptr;
+      // whole S row (128 fp32) into registers with one wait
+      uint32_t sr[4][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask) {
-            const int kc = k0 + c + i;
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sr[c]);
+      tmem_ld_wait();
+      if (need_mask) {  // rare path (diagonal / tail / padded keys): -inf on dead keys
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kc = k0 + c * 32 + i;
             const bool dead = kc >= p.Tk || (p.causal && kc > qpos) || (km && kc < p.Tk && km[kc]);
-            if (dead) s = -INFINITY;
+            if (dead) sr[c][i] = 0xff800000u;
           }
-          mx = fmaxf(mx, s);
         }
       }
-      const float m_new = fmaxf(m_ref, mx * p.scale_log2);
-      // lazy rescale, warp-uniform decision (tcgen05.ld/st are warp-collective)
-      const bool want = (m_new - m_ref > 8.0f) || (m_ref == -INFINITY && m_new > -INFINITY);
-      const bool do_rescale = __any_sync(0xffffffffu, want);
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) done: O valid, P smem free
-        tc_fence_after();
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
       }
-      if (do_rescale) {
-        const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+      const bool want = (m_new - m_ref > 8.0f) || (m_ref == -INFINITY && m_new > -INFINITY);
+      if (__any_sync(0xffffffffu, want)) {
+        const float f = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_new);
         l *= f;
         m_ref = m_new;
         if (j > 0) {
 #pragma unroll 1
           for (int c = 0; c < AT_D; c += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tO + lane_addr + c, v);
+            tmem_ld_32x32(tO + c, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st_32x32(tO + lane_addr + c, v);
+            tmem_st_32x32(tO + c, v);
           }
-          tmem_st_wait();
         }
       }
-      const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // pass 2: p = exp2(s*scale - m_ref) -> bf16 -> swizzled smem (K-major SW128: 16B chunk index ^= row & 7)
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c, v);
-        tmem_ld_wait();
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-          if (need_mask) {
-            const int kc = k0 + c + i;
-            const bool d0 = kc >= p.Tk || (p.causal && kc > qpos) || (km && kc < p.Tk && km[kc]);
-            const bool d1 = kc + 1 >= p.Tk || (p.causal && kc + 1 > qpos) || (km && kc + 1 < p.Tk && km[kc + 1]);
-            if (d0) s0 = -INFINITY;
-            if (d1) s1 = -INFINITY;
-          }
-          const float p0 = exp2f(s0 * p.scale_log2 - mref_safe);
-          const float p1 = exp2f(s1 * p.scale_log2 - mref_safe);
-          const uint32_t u = pack_bf16(p0, p1);
-          lsum += bf16_lo(u) + bf16_hi(u);  // sum what the tensor core will actually multiply
-          pk[i >> 1] = u;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, neg_m));
+          l0 += p0;
+          l1 += p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
         }
-        uint8_t* atom = prow + (c >> 6) * AT_HALF;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c & 63) >> 3) + ch;
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        }
+        // P chunk (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16): S is already in registers
+        tmem_st_32x16(tS + c * 16, pk);
       }
-      l += lsum;
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      l += l0 + l1;
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[t]);
     }
-    // ------------------------------ epilogue: O / l -> bf16 -> out[b, q, h*out_hd + d]
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
-    __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.Tq + q) * (static_cast<int64_t>(p.H) * p.out_hd) + h * p.out_hd;
+    if (n_kv_t > 0) {
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.Tq + q) * (static_cast<int64_t>(p.H) * p.out_hd) + h * p.out_hd;
 #pragma unroll 1
-    for (int c = 0; c < AT_D; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tO + lane_addr + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int c = 0; c < AT_D; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + c, v);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (c + g * 8 + 8 <= p.out_hd) {
-            float x[8];
+          for (int g = 0; g < 4; ++g) {
+            if (c + g * 8 + 8 <= p.out_hd) {
+              float x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]) * inv_l;
-            *reinterpret_cast<uint4*>(orow + c + g * 8) =
-                make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]) * inv_l;
+              *reinterpret_cast<uint4*>(orow + c + g * 8) =
+                  make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            }
           }
         }
       }
@@ -272,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,17 +433,17 @@ extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, v
   p.causal = causal;
   p.key_mask = key_mask;
   p.out = static_cast<__nv_bfloat16*>(out);
-  p.n_q_tiles = (Tq + AT_BM - 1) / AT_BM;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM) != cudaSuccess)
       return ARIA_ERR_CUDA;
     attr_set = true;
   }
+  p.n_q_tiles = (Tq + 2 * AT_BM - 1) / (2 * AT_BM);  // 256-row query pairs
   const int64_t grid = static_cast<int64_t>(B) * H * p.n_q_tiles;
   ARIA_CHECK_ARG(grid < (1ll << 31));
-  attn_fwd_kernel<<<static_cast<int>(grid), AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
-  return check_launch("attn_fwd_kernel");
+  attn_fwd2_kernel<<<static_cast<int>(grid), A2_THREADS, A2_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("attn_fwd2_kernel");
 }
 
 extern "C" int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, int32_t Tk) {

@@ -12,7 +12,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["gemm_dense", "gemm_mn", "gemm_mn_sweep", "swiglu", "heads", "routing", "rowwise", "attn", "attn_decode", "perf"]
+GROUPS = ["gemm_dense", "gemm_mn", "gemm_mn_sweep", "swiglu", "heads", "routing", "rowwise", "attn", "attn_decode", "perf", "perf_attn"]
 
 
 def rel(a, b):
@@ -290,6 +290,19 @@ def g_attn():
         torch.cuda.synchronize()
         ref = _attn_ref(q, k[:, :, :Tk], v[:, :, :Tk], scale, causal, mask)[..., :out_hd].reshape(B, Tq, H * out_hd)
         report(f"attn B{B} H{H} Tq{Tq} Tk{Tk} causal={causal} mask={masked} hd={out_hd}", o, ref, 2e-2)
+
+
+def g_perf_attn():
+    import torch
+    from aria_b200 import ops
+    dev = "cuda"
+    for (B, H, T, causal) in [(1, 20, 768, True), (1, 20, 8192, True), (1, 16, 4900, False), (1, 20, 32768, True)]:
+        q = torch.randn(B, H, T, 128, device=dev).bfloat16()
+        k = torch.randn(B, H, T, 128, device=dev).bfloat16()
+        v = torch.randn(B, H, T, 128, device=dev).bfloat16()
+        ms = _time(lambda: ops.attention(q, k, v, T, T, 128 ** -0.5, causal), iters=5)
+        fl = 4 * B * H * T * T * 128 * (0.5 if causal else 1.0)
+        print(f"  attention B{B} H{H} T{T} causal={causal}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
 def g_attn_decode():

@@ -1,0 +1,41 @@
+"""Tiny drivers for ncu captures: `attn` (ViT-shape attention), `attn_causal`, `fc1` (cfg-2 fc1 grouped GEMM + SwiGLU),
+`fc2`, `dense` (ViT fc1 GEMM with gelu)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from aria_b200 import ops, _lib as L
+dev = "cuda"
+mode = sys.argv[1]
+torch.manual_seed(0)
+if mode in ("attn", "attn_causal"):
+    B, H, T = (1, 16, 4900) if mode == "attn" else (1, 20, 8192)
+    q = torch.randn(B, H, T, 128, device=dev).bfloat16()
+    k = torch.randn(B, H, T, 128, device=dev).bfloat16()
+    v = torch.randn(B, H, T, 128, device=dev).bfloat16()
+    for _ in range(2):
+        ops.attention(q, k, v, T, T, 128 ** -0.5, mode == "attn_causal")
+elif mode in ("fc1", "fc2"):
+    E, d, I, T = 64, 2560, 1664, 768
+    rows = T * 6
+    g = torch.Generator().manual_seed(3)
+    counts = torch.randint(50, 95, (E,), generator=g)
+    counts[-1] += rows - counts.sum()
+    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]).to(torch.int32).to(dev)
+    if mode == "fc1":
+        w = (torch.randn(E, d, 2 * I, device=dev) * 0.02).bfloat16()
+        a = torch.randn(rows, d, device=dev).bfloat16()
+        for _ in range(3):
+            ops.grouped_gemm(a, w, off, swiglu=True)
+    else:
+        w = (torch.randn(E, I, d, device=dev) * 0.02).bfloat16()
+        a = torch.randn(rows, I, device=dev).bfloat16()
+        for _ in range(3):
+            ops.grouped_gemm(a, w, off)
+elif mode == "dense":
+    x = torch.randn(4900, 1152, device=dev).bfloat16()
+    w = (torch.randn(4304, 1152, device=dev) * 0.02).bfloat16()
+    b = torch.randn(4304, device=dev).bfloat16()
+    for _ in range(3):
+        ops.linear(x, w, b, act=L.ACT_GELU_TANH)
+torch.cuda.synchronize()
