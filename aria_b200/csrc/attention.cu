@@ -26,12 +26,7 @@ constexpr int AT_D = 128;    // head dim
 constexpr int AT_TILE = AT_BM * AT_D * 2;  // 32 KB
 constexpr int AT_HALF = AT_TILE / 2;       // one SW128 atom column: [128 rows][64 bf16]
 
-// ex2.approx: one MUFU op, no range-handling branches (inputs here are <= 8 and finite or -inf)
-ARIA_DEVICE float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+ARIA_DEVICE float fast_exp2(float x) { return fast_ex2(x); }
 
 struct AttnParams {
   int B, H, Tq, Tk;

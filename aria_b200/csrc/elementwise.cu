@@ -18,19 +18,20 @@ static inline int rows_grid(int64_t rows, int wpb) {
   return static_cast<int>(b);
 }
 
-// LlamaRMSNorm: h = x (+res, bf16-rounded); out = w * bf16(h * (1/sqrt(mean(h^2)+eps)))
-template <int MAXV>  // max uint4 per lane held in registers
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
+// LlamaRMSNorm: h = x (+res, bf16-rounded); out = w * bf16(h * (1/sqrt(mean(h^2)+eps))).
+// One 128-thread block per row (prefill batches are only a few hundred rows: a warp per row leaves the SMs idle).
+template <int MAXV>  // max uint4 per thread held in registers
+__global__ void __launch_bounds__(128) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
                                                       const uint4* __restrict__ w, uint4* __restrict__ out,
                                                       uint4* __restrict__ sum_out, int64_t rows, int vpr, float eps, float inv_d) {
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
-       r += static_cast<int64_t>(gridDim.x) * wpb) {
+  __shared__ float red[4];
+  const int tid = threadIdx.x;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     float h[MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+      const int v = tid + i * 128;
       if (v < vpr) {
         const uint4 q = x[r * vpr + v];
         const uint32_t a[4] = {q.x, q.y, q.z, q.w};
@@ -56,10 +57,14 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ 
       }
     }
     ss = warp_sum(ss);
+    __syncthreads();  // red[] free (previous row consumed)
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    ss = red[0] + red[1] + red[2] + red[3];
     const float rstd = 1.0f / sqrtf(ss * inv_d + eps);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+      const int v = tid + i * 128;
       if (v < vpr) {
         const uint4 q = __ldg(w + v);
         const uint32_t a[4] = {q.x, q.y, q.z, q.w};
@@ -236,18 +241,21 @@ using namespace aria;
 extern "C" int aria_rmsnorm(const void* x, const void* residual, const void* weight, void* out, void* sum_out, int64_t rows,
                             int32_t d, float eps, aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ARIA_CHECK_ARG(x && weight && out && d % 8 == 0 && d <= 32 * 8 * 16 && rows >= 0);
+  ARIA_CHECK_ARG(x && weight && out && d % 8 == 0 && d <= 128 * 8 * 4 && rows >= 0);
   if (rows == 0) return ARIA_OK;
   const int vpr = d / 8;
-  const int grid = rows_grid(rows, 8);
+  int64_t grid64 = rows;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (grid64 > cap) grid64 = cap;
+  const int grid = static_cast<int>(grid64);
 #define RMS(MAXV)                                                                                                   \
-  rmsnorm_kernel<MAXV><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(residual), \
+  rmsnorm_kernel<MAXV><<<grid, 128, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(residual), \
                                                  static_cast<const uint4*>(weight), static_cast<uint4*>(out),       \
                                                  static_cast<uint4*>(sum_out), rows, vpr, eps, 1.0f / d)
-  if (vpr <= 32 * 2) RMS(2);
-  else if (vpr <= 32 * 5) RMS(5);
-  else if (vpr <= 32 * 10) RMS(10);
-  else RMS(16);
+  if (vpr <= 128) RMS(1);
+  else if (vpr <= 256) RMS(2);
+  else if (vpr <= 384) RMS(3);
+  else RMS(4);
 #undef RMS
   return check_launch("rmsnorm_kernel");
 }

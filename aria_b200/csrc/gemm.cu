@@ -94,7 +94,7 @@ ARIA_DEVICE float act_apply(float x, int act) {
     // torch gelu(approximate="tanh"): one fp32 evaluation, rounded once by the caller
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     float inner = k0 * (x + k1 * x * x * x);
-    return 0.5f * x * (1.f + tanhf(inner));
+    return 0.5f * x * (1.f + fast_tanh(inner));
   }
   if (act == ARIA_ACT_GELU_NEW) {
     // transformers NewGELUActivation evaluated op by op on bf16 tensors (aria/model/projector.py:40-45):
@@ -103,7 +103,7 @@ ARIA_DEVICE float act_apply(float x, int act) {
     float t = bf16r(0.044715f * p3);
     t = bf16r(x + t);
     t = bf16r(0.7978845608028654f * t);
-    t = bf16r(tanhf(t));
+    t = bf16r(fast_tanh(t));
     t = bf16r(1.0f + t);
     float h = bf16r(0.5f * x);
     return h * t;
@@ -286,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 32; j += 2) {
             float g0 = bf16r(__uint_as_float(g[j])), g1 = bf16r(__uint_as_float(g[j + 1]));
             float u0 = bf16r(__uint_as_float(u[j])), u1 = bf16r(__uint_as_float(u[j + 1]));
-            float s0 = bf16r(g0 / (1.f + expf(-g0))), s1 = bf16r(g1 / (1.f + expf(-g1)));
+            float s0 = bf16r(fast_silu(g0)), s1 = bf16r(fast_silu(g1));
             o[j >> 1] = pack_bf16(s0 * u0, s1 * u1);
           }
           if (row_ok) {

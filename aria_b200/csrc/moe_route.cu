@@ -138,13 +138,11 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const uint4* __restri
 }
 
 // out[t] = bf16( sum_j bf16(y[dest[t*k+j]] * s[t,j]) ) (+ shared[t] with one more bf16 rounding).
+// One block per token, one 16-byte column per thread: the k gathered rows are k independent loads in flight.
 __global__ void __launch_bounds__(256) combine_kernel(const uint4* __restrict__ y, const int32_t* __restrict__ dest_row,
                                                       const __nv_bfloat16* __restrict__ scores, const uint4* __restrict__ shared_out,
                                                       uint4* __restrict__ out, int64_t T, int vec_per_row, int k) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T;
-       t += static_cast<int64_t>(gridDim.x) * wpb) {
+  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
     int rows[MAX_K];
     float sc[MAX_K];
 #pragma unroll
@@ -154,15 +152,20 @@ __global__ void __launch_bounds__(256) combine_kernel(const uint4* __restrict__ 
         sc[j] = __bfloat162float(scores[t * k + j]);
       }
     }
-    for (int v = lane; v < vec_per_row; v += 32) {
+    for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
+      uint4 q[MAX_K];
+#pragma unroll
+      for (int j = 0; j < MAX_K; ++j)
+        if (j < k) q[j] = __ldg(y + static_cast<int64_t>(rows[j]) * vec_per_row + v);
+      uint4 sh = make_uint4(0, 0, 0, 0);
+      if (shared_out) sh = __ldg(shared_out + t * vec_per_row + v);
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
       for (int j = 0; j < MAX_K; ++j) {
         if (j < k) {
-          const uint4 q = __ldg(y + static_cast<int64_t>(rows[j]) * vec_per_row + v);
-          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+          const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             acc[2 * i] += bf16r(bf16_lo(w[i]) * sc[j]);
@@ -173,8 +176,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const uint4* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = bf16r(acc[i]);
       if (shared_out) {
-        const uint4 q = __ldg(shared_out + t * vec_per_row + v);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t w[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           acc[2 * i] += bf16_lo(w[i]);
@@ -270,7 +272,9 @@ extern "C" int aria_unpermute_combine(const void* y, const int32_t* dest_row, co
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ARIA_CHECK_ARG(y && dest_row && scores && out && d % 8 == 0 && k >= 1 && k <= MAX_K && T >= 0);
   if (T == 0) return ARIA_OK;
-  combine_kernel<<<grid_for_warps(T, 8), 256, 0, stream>>>(static_cast<const uint4*>(y), dest_row,
+  int64_t cgrid = T;
+  if (cgrid > static_cast<int64_t>(sm_count()) * 16) cgrid = static_cast<int64_t>(sm_count()) * 16;
+  combine_kernel<<<static_cast<int>(cgrid), 256, 0, stream>>>(static_cast<const uint4*>(y), dest_row,
                                                            static_cast<const __nv_bfloat16*>(scores),
                                                            static_cast<const uint4*>(shared), static_cast<uint4*>(out), T,
                                                            d / 8, k);

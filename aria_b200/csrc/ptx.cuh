@@ -188,6 +188,25 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 }
 
 // ---------------------------------------------------------------- small numeric helpers
+// Single-instruction MUFU approximations (max rel. error ~2^-11 / 2^-22): results are rounded to bf16 (2^-9) right
+// after, and the branchy libm versions cost >10x more issue slots + I-cache in fused epilogues.
+ARIA_DEVICE float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+ARIA_DEVICE float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+ARIA_DEVICE float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(x) = x * sigmoid(x) = x / (1 + 2^(-x*log2 e))
+ARIA_DEVICE float fast_silu(float x) { return x * fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
 ARIA_DEVICE float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 ARIA_DEVICE uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -119,6 +119,50 @@ class AriaForConditionalGeneration(nn.Module):
         return torch.cat([input_ids.to(tokens[0].device), torch.stack(tokens, 1)], dim=1)
 
 
+class GraphedPrefill:
+    """CUDA-graph capture of one prefill `forward()` for fixed shapes (streams + graphs instead of a tracing
+    compiler): the whole ViT -> projector -> merge -> LM chain has no host sync, so it is captured once and replayed.
+
+        g = GraphedPrefill(model, input_ids_host, pixel_values_host)      # warm-up + capture
+        logits = g(input_ids_host, pixel_values_host)                      # H2D copies + replay; logits on device
+        logits = g.replay()                                                # inputs already resident in HBM
+    """
+
+    def __init__(self, model: "AriaForConditionalGeneration", input_ids: torch.Tensor, pixel_values: torch.Tensor,
+                 num_logits_to_keep: int = 1):
+        self.model = model
+        dev = model.device
+        self.ids_dev = torch.empty(input_ids.shape, dtype=torch.int64, device=dev)
+        self.pv_dev = torch.empty(pixel_values.shape, dtype=bf16, device=dev)
+        self.ids_dev.copy_(input_ids)
+        self.pv_dev.copy_(pixel_values)
+        self.n_image_tokens = int((input_ids == model.config.image_token_index).sum())
+        ids_host = input_ids.cpu()
+        kw = dict(num_logits_to_keep=num_logits_to_keep, input_ids_host=ids_host)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                model(self.ids_dev, self.pv_dev, None, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = model(self.ids_dev, self.pv_dev, None, **kw).logits
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.logits
+
+    def __call__(self, input_ids: torch.Tensor, pixel_values: torch.Tensor) -> torch.Tensor:
+        if not input_ids.is_cuda:  # same ValueError contract as forward() (modeling_aria.py:268-271), checked on the host
+            n = int((input_ids == self.model.config.image_token_index).sum())
+            if n != self.n_image_tokens:
+                raise ValueError(f"Image features and image tokens do not match: tokens: {n}, features {self.n_image_tokens}")
+        self.ids_dev.copy_(input_ids, non_blocking=True)
+        self.pv_dev.copy_(pixel_values, non_blocking=True)
+        return self.replay()
+
+
 def init_random_(model: nn.Module, seed: int = 0, std: float = 0.02):
     """Random-init (no checkpoint offline): N(0, std^2) for matrices / embeddings / biases / queries, 1 for the
     norm scales (the only 1-D parameters named `weight`)."""

@@ -210,8 +210,9 @@ class KVCache:
     """Static per-layer KV cache in the HF layout [B, H, T_max, head_dim] (modeling_aria.py:49-50)."""
 
     def __init__(self, n_layers, B, H, T_max, hd, device):
-        self.k = [torch.zeros(B, H, T_max, hd, dtype=bf16, device=device) for _ in range(n_layers)]
-        self.v = [torch.zeros(B, H, T_max, hd, dtype=bf16, device=device) for _ in range(n_layers)]
+        # rows >= seq_len are never read (the attention TMA maps cover the valid rows only), so no zero-fill
+        self.k = [torch.empty(B, H, T_max, hd, dtype=bf16, device=device) for _ in range(n_layers)]
+        self.v = [torch.empty(B, H, T_max, hd, dtype=bf16, device=device) for _ in range(n_layers)]
         self.q = torch.empty(B, H, T_max, hd, dtype=bf16, device=device)  # rows [seq_len, seq_len+T) used per step
         self.seq_len = 0
         self.T_max = T_max

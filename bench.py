@@ -180,7 +180,7 @@ def run_aria(args, rank, local_rank, world):
 
     from aria_b200 import _lib as L
     from aria_b200 import ops
-    from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration, init_random_
+    from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration, GraphedPrefill, init_random_
     from oracle import configs as C  # shapes only (plain dict of model dimensions)
 
     L.load()  # fail loudly if the CUDA extension is missing
@@ -218,12 +218,18 @@ def run_aria(args, rank, local_rank, world):
 
     ops.grouped_gemm = timed_gg
 
-    def step_resident():
-        # device-resident inputs; the host copy of the ids only feeds the image-token count check (no device sync)
+    # public API: eager forward() for the instrumented leg, GraphedPrefill (CUDA-graph replay of the same forward)
+    # for the throughput legs
+    def step_eager():
         return model(ids_dev, pv_dev, None, num_logits_to_keep=1, input_ids_host=ids_host).logits
 
+    graphed = GraphedPrefill(model, ids_host, pv_host, num_logits_to_keep=1)
+
+    def step_resident():
+        return graphed.replay()  # inputs already resident in HBM
+
     def step_e2e():
-        out = model(ids_host, pv_host, None, num_logits_to_keep=1).logits
+        out = graphed(ids_host, pv_host)            # H2D of ids + pixels from pinned host memory, then replay
         logits_host.copy_(out, non_blocking=False)  # D2H read of the step's result (synchronises)
         return logits_host
 
@@ -238,8 +244,10 @@ def run_aria(args, rank, local_rank, world):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # kernels per step (counted on one eager forward; the graph replays exactly these launches)
     l0 = L.launch_count
-    rec["on"] = True
+    step_eager()
+    launches_per_step = L.launch_count - l0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -247,9 +255,19 @@ def run_aria(args, rank, local_rank, world):
         step_resident()
     e1.record()
     barrier()
-    rec["on"] = False
-    launches = L.launch_count - l0
     ms = e0.elapsed_time(e1) / args.steps
+    launches = launches_per_step * args.steps
+    # dominant kernel, timed live with CUDA events on the launching stream over the same K steps (eager launches of
+    # the identical kernels; events cannot be recorded inside a graph replay)
+    rec["on"] = True
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for _ in range(args.steps):
+        step_eager()
+    x1.record()
+    barrier()
+    rec["on"] = False
+    ms_eager = x0.elapsed_time(x1) / args.steps
     fc1_ms = [a.elapsed_time(b) for a, b, _ in rec["ev"]]
     fc1_rows = rec["ev"][0][2] if rec["ev"] else 0
 
@@ -283,7 +301,8 @@ def run_aria(args, rank, local_rank, world):
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": peak_src, "bytes_per_launch": fc1_bytes,
                 "avg_launch_ms": fc1_avg, "launches_timed": len(fc1_ms),
-                "share_of_step": sum(fc1_ms) / args.steps / ms if fc1_ms else None}
+                "share_of_step": sum(fc1_ms) / args.steps / ms_eager if fc1_ms else None,
+                "eager_ms_per_step": ms_eager}
     line = {"metric": METRIC, "value": world * T_TOTAL / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -293,7 +312,8 @@ def run_aria(args, rank, local_rank, world):
             "e2e": {"value": world * T_TOTAL / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pv_host.numel() * 2 + ids_host.numel() * 8,
                     "d2h_bytes_per_step": logits_host.numel() * 2},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "impl": "aria_b200"}
+            "gpu_launches": launches, "launch_mode": "CUDA graph replay of the eager forward (same kernels)",
+            "clocks": clocks, "roofline": roofline, "impl": "aria_b200"}
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference()
         ref.sample()  # warm-up
