@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
     _fields_ = [
         ("a", vp), ("lda", i64), ("m", i64), ("n", i64), ("k", i64),
         ("b", vp * 3), ("n_seg", i32), ("b_layout", i32),
-        ("num_groups", i32), ("group_offsets", vp),
+        ("num_groups", i32), ("group_offsets", vp), ("group_mod", i32),
         ("epilogue", i32), ("act", i32),
         ("bias", vp * 3), ("residual", vp), ("ldr", i64),
         ("out", vp * 3), ("ldo", i64),

@@ -45,21 +45,26 @@ ARIA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (kernel error) instead of hanging the GPU box.
+// Bounded wait: a broken pipeline traps (kernel error) after ~2 s instead of hanging the GPU box.
 ARIA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
-  uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0; ; ++spin) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     if (ok) return;
-    if (spin > (1u << 26)) {  // each failed try_wait already sleeps up to the HW time limit
-      printf("aria_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, addr, parity);
-      __trap();
+    if ((spin & 0xFFF) == 0xFFF) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) {
+        printf("aria_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr,
+               parity);
+        __trap();
+      }
     }
   }
 }
@@ -159,6 +164,61 @@ ARIA_DEVICE void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
         "r"(taddr) : "memory");
 }
 ARIA_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- 2-CTA (cta_group::2) variants and cluster helpers
+ARIA_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+ARIA_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster (shared::cluster window)
+ARIA_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+ARIA_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared),
+// destination = this CTA's shared memory.
+ARIA_DEVICE void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+ARIA_DEVICE void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols) : "memory");
+}
+ARIA_DEVICE void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+ARIA_DEVICE void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem of both CTAs, N/2 each]; leader CTA issues.
+ARIA_DEVICE void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in BOTH CTAs of the pair once the prior MMAs have completed
+ARIA_DEVICE void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (64-bit), SWIZZLE_128B (layout_type = 2 at bits [61,64)), version = 1

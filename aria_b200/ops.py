@@ -85,19 +85,21 @@ def linear_swiglu(x: torch.Tensor, gate_w: torch.Tensor, up_w: torch.Tensor) -> 
 
 
 def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu: bool = False,
-                 dbg=(0, 0, 0)) -> torch.Tensor:
+                 dbg=(0, 0, 0), group_mod: int = 0) -> torch.Tensor:
     """out[off[e]:off[e+1]] = a[off[e]:off[e+1]] @ b[e]; b [E, K, N] (GroupedGEMM.weight, moe_lm.py:465).
     swiglu=True fuses `glu` (moe_lm.py:505-507): b has 2I columns, out has I."""
     _chk(a), _chk(b), _chk(offsets, torch.int32)
     rows, K = a.shape
     E, Kb, Nb = b.shape
-    assert Kb == K and offsets.numel() == E + 1
+    G = offsets.numel() - 1  # groups; with group_mod, group g multiplies by weight block g % group_mod
+    assert Kb == K and (G == E if not group_mod else (group_mod == E and G % E == 0))
     N = Nb // 2 if swiglu else Nb
     out = torch.empty((rows, N), dtype=bf16, device=a.device)
     d = L.GemmDesc()
     d.a, d.lda, d.m, d.n, d.k = a.data_ptr(), K, rows, N, K
     d.b[0] = b.data_ptr()
-    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GKN, E
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GKN, G
+    d.group_mod = group_mod
     d.group_offsets = offsets.data_ptr()
     d.epilogue = L.EPI_SWIGLU if swiglu else L.EPI_LINEAR
     d.out[0], d.ldo = out.data_ptr(), N

@@ -57,6 +57,8 @@ typedef struct aria_gemm_desc {
    * int32) are the row offsets of each expert's contiguous row block inside A / out.                   */
   int32_t num_groups;
   const int32_t* group_offsets;
+  int32_t group_mod;       /* GKN only: group g uses weight block g % group_mod (0 = identity). Expert parallelism
+                            * receives rows grouped by (source rank, local expert): num_groups = W*E_loc, mod = E_loc */
   /* epilogue */
   int32_t epilogue;
   int32_t act;

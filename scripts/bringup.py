@@ -334,6 +334,35 @@ def _time(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def g_perf_gemm():
+    import torch
+    from aria_b200 import ops, _lib as L
+    dev = "cuda"
+    torch.manual_seed(8)
+    for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 8192), (4900, 4304, 1152), (4900, 1152, 4304), (4900, 1152, 1152),
+                      (768, 2560, 2560), (768, 3328, 2560)]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = torch.randn(N, K, device=dev).bfloat16()
+        b = torch.randn(N, device=dev).bfloat16()
+        ms = _time(lambda: ops.linear(x, w))
+        ms_g = _time(lambda: ops.linear(x, w, b, act=L.ACT_GELU_TANH))
+        ms_t = _time(lambda: x @ w.t())
+        print(f"  dense {M}x{N}x{K}: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.1f} TFLOP/s  (+bias+gelu {ms_g:.3f} ms)  (cuBLAS {ms_t:.3f} ms = {2 * M * N * K / ms_t / 1e9:.1f})", flush=True)
+    E, d, I = 64, 2560, 1664
+    fc1 = (torch.randn(E, d, 2 * I, device=dev) * 0.02).bfloat16()
+    fc2 = (torch.randn(E, I, d, device=dev) * 0.02).bfloat16()
+    for T in (768, 8192):
+        rows = T * 6
+        counts = torch.full((E,), rows // E, dtype=torch.int64)
+        off = torch.tensor([0] + counts.cumsum(0).tolist(), dtype=torch.int32, device=dev)
+        a = torch.randn(rows, d, device=dev).bfloat16()
+        h = torch.randn(rows, I, device=dev).bfloat16()
+        ms1 = _time(lambda: ops.grouped_gemm(a, fc1, off, swiglu=True))
+        ms2 = _time(lambda: ops.grouped_gemm(h, fc2, off))
+        fl1, fl2 = 2 * rows * d * 2 * I, 2 * rows * I * d
+        print(f"  grouped T={T}: fc1+swiglu {ms1:.3f} ms ({fl1 / ms1 / 1e9:.1f} TFLOP/s)  fc2 {ms2:.3f} ms ({fl2 / ms2 / 1e9:.1f} TFLOP/s)", flush=True)
+
+
 def g_perf():
     import torch
     from aria_b200 import ops
