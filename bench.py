@@ -297,9 +297,14 @@ def run_aria(args, rank, local_rank, world):
     fc1_bytes = E * d * 2 * I * 2 + fc1_rows * d * 2 + fc1_rows * I * 2  # weights + A read + out write
     fc1_avg = statistics.mean(fc1_ms) if fc1_ms else float("nan")
     achieved = fc1_bytes / (fc1_avg * 1e-3) / 1e9
+    try:  # DRAM traffic of the same kernel from the committed `ncu --set full` capture (per launch)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "fc1_traffic.json")))
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "gemm_kernel<128,MN-major,SWIGLU> (fc1 grouped expert GEMM)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": fc1_bytes,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": fc1_bytes,
                 "avg_launch_ms": fc1_avg, "launches_timed": len(fc1_ms),
                 "share_of_step": sum(fc1_ms) / args.steps / ms_eager if fc1_ms else None,
                 "eager_ms_per_step": ms_eager}

@@ -86,7 +86,7 @@ def ep_worker(rank, world, port, backend_name, device_kind, tc, T, dtype_name, r
         torch.cuda.synchronize()
     lg = parts["logits"].float().sort(1, descending=True).values
     k = tc["moe_topk"]
-    safe = (lg[:, k - 1] - lg[:, k]) / lg.abs().amax(1) > 2 ** -5
+    safe = (lg[:, k - 1] - lg[:, k]) / lg.abs().amax(1) > 2 ** -6
     err = (got - want.float()).abs().amax(-1)
     scale = float(want.float().abs().max())
     torch.save({"err_safe": float(err[safe].max()) / scale, "err_all": float(err.max()) / scale,

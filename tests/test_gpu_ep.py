@@ -19,4 +19,4 @@ def test_ep_forward_two_gpus(E, k, T, d, I):
         mp.spawn(ep_worker, args=(2, free_port(), "cuda", "cuda", tc, T, "bfloat16", tmp), nprocs=2, join=True)
         for r in range(2):
             res = torch.load(f"{tmp}/rank{r}.pt")
-            assert res["err_safe"] <= 1e-2 and res["n_safe"] >= res["n"] // 2, res
+            assert res["err_safe"] <= 1e-2 and res["n_safe"] >= res["n"] // 4, res
