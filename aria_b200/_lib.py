@@ -60,7 +60,7 @@ SIGNATURES = {
     "aria_im2col_patches": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "aria_add_pos_embedding": (i32, [vp, vp, vp, vp, i64, i32, vp]),
     "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),
-    "aria_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i64, f32, vp, i64, vp]),
+    "aria_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i64, vp]),
     "aria_attention_decode_workspace_bytes": (i64, [i32, i32, i32]),
 }
 

@@ -28,9 +28,12 @@ constexpr int AT_HALF = AT_TILE / 2;       // one SW128 atom column: [128 rows][
 
 ARIA_DEVICE float fast_exp2(float x) { return fast_ex2(x); }
 
+// (A polynomial exp2 on the FMA pipes for a quarter of the elements — the FA4 trick — was measured and LOST 20 %: this
+// softmax is issue-slot bound, not MUFU bound; see profiles/r01_attention_notes.txt.)
 struct AttnParams {
   int B, H, Tq, Tk;
   int out_hd;
+  int hd_eff;  // head dim actually contracted / produced (multiple of 16): 128 for the LM, 80 for the 72-wide ViT heads
   float scale_log2;
   int causal;
   const uint8_t* key_mask;  // [B, Tk] 1 = masked out
@@ -128,13 +131,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(AT_BM, AT_D, false, true);
+      const uint32_t idesc_pv = make_idesc_bf16(AT_BM, p.hd_eff, false, true);  // N = hd_eff output columns
+      const int qk_steps = p.hd_eff / 16;                                       // columns >= hd_eff are zero padding
       auto issue_qk = [&](int t, int j) {
         const uint32_t aQ = smem_u32(sQ + t * AT_TILE);
         const uint32_t aK = smem_u32(sK + (j & 1) * AT_TILE);
         const uint32_t tS = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k) {
+          if (k >= qk_steps) break;
           const uint32_t off = (k >> 2) * AT_HALF + (k & 3) * 32;
           umma_bf16_ss(tS, make_smem_desc(aQ + off, 16, 1024), make_smem_desc(aK + off, 16, 1024), idesc_qk, k ? 1u : 0u);
         }
@@ -235,7 +240,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_ref = m_new;
         if (j > 0) {
 #pragma unroll 1
-          for (int c = 0; c < AT_D; c += 32) {
+          for (int c = 0; c < p.hd_eff; c += 32) {
             uint32_t v[32];
             tmem_ld_32x32(tO + c, v);
             tmem_ld_wait();
@@ -252,8 +257,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, neg_m));
+          const float x0 = fmaf(__uint_as_float(sr[c][i]), p.scale_log2, neg_m);
+          const float x1 = fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, neg_m);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);
           l0 += p0;
           l1 += p1;
           pk[i >> 1] = pack_bf16(p0, p1);
@@ -272,7 +279,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
       __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.Tq + q) * (static_cast<int64_t>(p.H) * p.out_hd) + h * p.out_hd;
 #pragma unroll 1
-      for (int c = 0; c < AT_D; c += 32) {
+      for (int c = 0; c < p.out_hd; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tO + c, v);
         tmem_ld_wait();
@@ -303,14 +310,15 @@ constexpr int DEC_SPLIT_KEYS = 256;
 
 __global__ void __launch_bounds__(128) attn_decode_partial(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                                                            const __nv_bfloat16* __restrict__ vc, float* __restrict__ ws, int H, int Tk,
-                                                           int64_t kv_stride_b, int64_t kv_stride_h, float scale_log2, int splits) {
+                                                           int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b,
+                                                           int64_t kv_stride_h, float scale_log2, int splits) {
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / H, h = bh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_begin = split * DEC_SPLIT_KEYS, k_end = min(Tk, k_begin + DEC_SPLIT_KEYS);
   const __nv_bfloat16* kbase = kc + b * kv_stride_b + h * kv_stride_h;
   const __nv_bfloat16* vbase = vc + b * kv_stride_b + h * kv_stride_h;
-  const uint2 qv = *reinterpret_cast<const uint2*>(q + static_cast<int64_t>(bh) * AT_D + lane * 4);
+  const uint2 qv = *reinterpret_cast<const uint2*>(q + b * q_stride_b + h * q_stride_h + lane * 4);
   const float q0 = bf16_lo(qv.x) * scale_log2, q1 = bf16_hi(qv.x) * scale_log2, q2 = bf16_lo(qv.y) * scale_log2,
               q3 = bf16_hi(qv.y) * scale_log2;
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -424,6 +432,7 @@ extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, v
   p.Tq = Tq;
   p.Tk = Tk;
   p.out_hd = out_hd;
+  p.hd_eff = (out_hd + 15) / 16 * 16;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.key_mask = key_mask;
@@ -447,16 +456,16 @@ extern "C" int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, i
 }
 
 extern "C" int aria_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tk,
-                                     int64_t kv_stride_b, int64_t kv_stride_h, float scale, void* workspace,
-                                     int64_t workspace_bytes, aria_stream_t stream_) {
+                                     int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b, int64_t kv_stride_h,
+                                     float scale, void* workspace, int64_t workspace_bytes, aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ARIA_CHECK_ARG(q && k && v && out && workspace && B > 0 && H > 0 && Tk > 0);
+  ARIA_CHECK_ARG(q && k && v && out && workspace && B > 0 && H > 0 && Tk > 0 && q_stride_b % 4 == 0 && q_stride_h % 4 == 0);
   ARIA_CHECK_ARG(workspace_bytes >= aria_attention_decode_workspace_bytes(B, H, Tk));
   const int splits = (Tk + DEC_SPLIT_KEYS - 1) / DEC_SPLIT_KEYS;
   dim3 grid(B * H, splits);
   attn_decode_partial<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
                                                 static_cast<const __nv_bfloat16*>(v), static_cast<float*>(workspace), H, Tk,
-                                                kv_stride_b, kv_stride_h, scale * 1.4426950408889634f, splits);
+                                                q_stride_b, q_stride_h, kv_stride_b, kv_stride_h, scale * 1.4426950408889634f, splits);
   int rc = check_launch("attn_decode_partial");
   if (rc) return rc;
   attn_decode_merge<<<B * H, 128, 0, stream>>>(static_cast<const float*>(workspace), static_cast<__nv_bfloat16*>(out), splits);

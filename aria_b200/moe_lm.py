@@ -248,8 +248,7 @@ class AriaAttention(nn.Module):
         Tk = pos0 + T
         scale = hd ** -0.5
         if T == 1:
-            qd = q[:, :, pos0, :].contiguous()
-            o = ops.attention_decode(qd, kc, vc, Tk, scale).view(B, 1, d)
+            o = ops.attention_decode(q[:, :, pos0, :], kc, vc, Tk, scale).view(B, 1, d)  # strided view, no copy
         else:
             o = ops.attention(q[:, :, pos0:], kc, vc, T, Tk, scale, causal=True)
         return ops.linear(o, self.o_proj.weight, residual=residual)

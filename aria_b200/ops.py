@@ -306,14 +306,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tq: int, Tk: in
 
 
 def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tk: int, scale: float) -> torch.Tensor:
-    """q [B,H,128] (contiguous), cache k/v [B,H,T_max,128] -> out [B, H*128]."""
-    _chk(q), _chk(k), _chk(v)
+    """q [B,H,128] (any strides with a contiguous last dim, e.g. a row of the q staging buffer), cache k/v
+    [B,H,T_max,128] -> out [B, H*128]."""
+    _chk(k), _chk(v)
+    if not (q.is_cuda and q.dtype == bf16 and q.stride(-1) == 1 and q.data_ptr() % 8 == 0):
+        raise RuntimeError("attention_decode: q must be a CUDA bf16 tensor with a contiguous last dim")
     B, H = q.shape[0], q.shape[1]
     lib = L.load()
     ws_bytes = lib.aria_attention_decode_workspace_bytes(B, H, Tk)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
     out = torch.empty((B, H * 128), dtype=bf16, device=q.device)
     with torch.cuda.device(q.device):
-        L.check(lib.aria_attention_decode(_p(q), _p(k), _p(v), _p(out), B, H, Tk, k.stride(0), k.stride(1), scale, _p(ws),
-                                          ws_bytes, _stream(q)), "attention_decode")
+        L.check(lib.aria_attention_decode(_p(q), _p(k), _p(v), _p(out), B, H, Tk, q.stride(0), q.stride(1), k.stride(0),
+                                          k.stride(1), scale, _p(ws), ws_bytes, _stream(q)), "attention_decode")
     return out

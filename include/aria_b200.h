@@ -159,11 +159,11 @@ int aria_attention_fwd(const void* q, const void* k, const void* v, void* out, c
                        int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t q_stride_b, int64_t q_stride_h,
                        int64_t kv_stride_b, int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal,
                        aria_stream_t stream);
-/* Single-token decode against a KV cache (HBM-bound, split-KV): q [B,H,128], cache [B,H,Tk_max,128].
- * workspace: B*H*splits*(128+2) floats. */
+/* Single-token decode against a KV cache (HBM-bound, split-KV): q element (b,h,:) at q + b*q_stride_b + h*q_stride_h
+ * (128 contiguous bf16), cache [B,H,Tk_max,128], out [B, H*128].  workspace: B*H*splits*(128+2) floats. */
 int aria_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tk,
-                          int64_t kv_stride_b, int64_t kv_stride_h, float scale, void* workspace,
-                          int64_t workspace_bytes, aria_stream_t stream);
+                          int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b, int64_t kv_stride_h, float scale,
+                          void* workspace, int64_t workspace_bytes, aria_stream_t stream);
 int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, int32_t Tk);
 
 #ifdef __cplusplus
