@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaria_b200.so")
 
 ARIA_OK = 0
-B_NK, B_GKN = 0, 1
+B_NK, B_GKN, B_GNK = 0, 1, 2
 EPI_LINEAR, EPI_SWIGLU, EPI_HEADS = 0, 1, 2
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_NEW = 0, 1, 2
 
@@ -49,7 +49,12 @@ SIGNATURES = {
     "aria_offsets_from_counts": (i32, [vp, vp, i32, vp]),
     "aria_router_topk": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "aria_route_from_logits": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
-    "aria_build_permutation": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "aria_build_permutation": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "aria_grouped_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i64, i64, i64, i32, vp]),
+    "aria_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
+    "aria_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
+    "aria_combine_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "aria_router_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_permute_rows": (i32, [vp, vp, vp, i64, i32, vp]),
     "aria_unpermute_combine": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_rmsnorm": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, vp]),

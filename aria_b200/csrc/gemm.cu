@@ -98,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int col = n_idx * BN;
               const int seg = col / p.N;
               const CUtensorMap* tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N);
+              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + grp * p.b_group_rows);
             }
           }
           if (++stage == STAGES) {
@@ -225,15 +225,19 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   ARIA_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out[0]) & 15) == 0);
   if (d->m == 0) return ARIA_OK;
   const bool b_mn = d->b_layout == ARIA_B_GKN;
+  const bool b_gnk = d->b_layout == ARIA_B_GNK;
   const bool swiglu = d->epilogue == ARIA_EPI_SWIGLU;
   if (b_mn) {
     ARIA_CHECK_ARG(d->n_seg == 1);
-    ARIA_CHECK_ARG(d->k % BK == 0);  // k-blocks must not straddle experts in the flattened [G*K, N] view
+    // k-blocks must not straddle experts in the flattened [G*K, N] view (a single group has no neighbour: TMA zero-fills)
+    ARIA_CHECK_ARG(d->k % BK == 0 || (d->num_groups == 1 && d->group_mod == 0));
     ARIA_CHECK_ARG(d->n % 64 == 0);
     ARIA_CHECK_ARG(d->epilogue != ARIA_EPI_HEADS);
   } else {
     ARIA_CHECK_ARG(d->num_groups == 1 || d->n_seg == 1);
     if (swiglu) ARIA_CHECK_ARG(d->n_seg == 2 && d->b[1]);
+    if (b_gnk) ARIA_CHECK_ARG(d->n_seg == 1 && !swiglu && d->epilogue == ARIA_EPI_LINEAR && d->n % 128 == 0);
+    else ARIA_CHECK_ARG(d->num_groups == 1);
   }
   if (d->num_groups > 1) ARIA_CHECK_ARG(d->group_offsets != nullptr);
 
@@ -244,6 +248,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   p.num_groups = d->num_groups;
   p.group_offsets = d->group_offsets;
   p.group_mod = d->group_mod;
+  p.b_group_rows = b_gnk ? static_cast<int>(d->n) : 0;
   p.n_seg = swiglu ? 1 : d->n_seg;
   p.act = d->act;
   for (int i = 0; i < 3; ++i) {
@@ -302,7 +307,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     // 2-CTA pays off with 256 x 256 tiles (twice the flops per byte pulled from L2, measured 1.28-1.38 PFLOP/s vs
     // 0.84 for 128 x 128); with too few such tiles (< ~1.3 waves of CTA pairs) the 1-CTA kernel fills the SMs better.
     const int64_t out_bn256 = swiglu ? 128 : 256;
-    const bool divisible = swiglu ? (d->n % 128 == 0) : (d->n_seg == 1 || d->n % 256 == 0);
+    const bool divisible = swiglu ? (d->n % 128 == 0) : ((d->n_seg == 1 && !b_gnk) || d->n % 256 == 0);
     const int64_t m_tiles256 = (d->num_groups == 1) ? (d->m + 255) / 256 : (d->m / 256 + d->num_groups / 2);
     const int64_t tiles256 = m_tiles256 * ((n_out_total + out_bn256 - 1) / out_bn256);
     if (divisible && tiles256 * 10 >= 13 * (sm_count() / 2)) {
@@ -329,7 +334,8 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     if (two_cta && !swiglu) box_rows = BN / 2;
     for (int s = 0; s < 3; ++s) {
       const void* ptr = s < nb ? d->b[s] : d->b[0];
-      rc = make_tmap_2d(&tmB[s], ptr, d->k, d->n, d->k * 2, BK, box_rows);
+      const uint64_t b_rows = b_gnk ? static_cast<uint64_t>(d->num_groups) * d->n : d->n;
+      rc = make_tmap_2d(&tmB[s], ptr, d->k, b_rows, d->k * 2, BK, box_rows);
       if (rc) return rc;
     }
   }

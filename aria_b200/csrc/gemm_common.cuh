@@ -29,6 +29,7 @@ struct GemmParams {
   int M, N, K;  // N = output columns per segment
   int num_groups;
   const int32_t* group_offsets;
+  int b_group_rows;  // K-major grouped weights [G, N, K]: B row of (group g, column c) is g*b_group_rows + c (0: dense)
   int group_mod;  // weight block of group g is g % group_mod (0: identity) — expert-parallel (src rank, expert) groups
   int n_seg;
   int act;

@@ -80,20 +80,22 @@ __global__ void __launch_bounds__(256) route_kernel(const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(1024) permutation_kernel(const int32_t* __restrict__ top_idx,
                                                            const int32_t* __restrict__ counts,
                                                            int32_t* __restrict__ offsets, int32_t* __restrict__ dest_row,
-                                                           int32_t* __restrict__ src_token, int64_t n, int E, int k) {
+                                                           int32_t* __restrict__ src_token, int64_t n, int E, int k, int align) {
   const int e = blockIdx.x;
   __shared__ int warp_cnt[32];
   __shared__ int base_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
+    // each expert's block starts on a multiple of `align` rows (1 for inference; 16 in training so that the
+    // wgrad GEMM's 16-row K steps never straddle two experts); pad rows keep src_token = -1
     int acc = 0;
-    for (int i = 0; i < e; ++i) acc += counts[i];
+    for (int i = 0; i < e; ++i) acc += (counts[i] + align - 1) / align * align;
     base_s = acc;
     if (e == 0) {
       int a = 0;
       for (int i = 0; i < E; ++i) {
         offsets[i] = a;
-        a += counts[i];
+        a += (counts[i] + align - 1) / align * align;
       }
       offsets[E] = a;
     }
@@ -131,8 +133,13 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const uint4* __restri
   const int wpb = blockDim.x >> 5;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
        r += static_cast<int64_t>(gridDim.x) * wpb) {
-    const uint4* src = x + static_cast<int64_t>(src_token[r]) * vec_per_row;
+    const int st = src_token[r];
     uint4* dst = out + r * vec_per_row;
+    if (st < 0) {  // alignment pad row (training-mode layout): zeros
+      for (int v = lane; v < vec_per_row; v += 32) dst[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const uint4* src = x + static_cast<int64_t>(st) * vec_per_row;
     for (int v = lane; v < vec_per_row; v += 32) dst[v] = __ldg(src + v);
   }
 }
@@ -249,11 +256,16 @@ extern "C" int aria_router_topk(const void* x, const void* w_router, void* logit
 }
 
 extern "C" int aria_build_permutation(const int32_t* top_idx, const int32_t* counts, int32_t* offsets, int32_t* dest_row,
-                                      int32_t* src_token, int64_t T, int32_t E, int32_t k, aria_stream_t stream_) {
+                                      int32_t* src_token, int64_t T, int32_t E, int32_t k, int32_t row_align,
+                                      aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ARIA_CHECK_ARG(top_idx && counts && offsets && dest_row && src_token);
-  ARIA_CHECK_ARG(E >= 1 && k >= 1 && T >= 0 && T * k < (1ll << 31));
-  permutation_kernel<<<E, 1024, 0, stream>>>(top_idx, counts, offsets, dest_row, src_token, T * k, E, k);
+  ARIA_CHECK_ARG(E >= 1 && k >= 1 && T >= 0 && T * k < (1ll << 31) && row_align >= 1);
+  if (row_align > 1) {  // src_token has T*k + E*(row_align-1) slots; pad rows stay -1
+    const size_t slots = static_cast<size_t>(T) * k + static_cast<size_t>(E) * (row_align - 1);
+    if (cudaMemsetAsync(src_token, 0xFF, slots * sizeof(int32_t), stream) != cudaSuccess) return ARIA_ERR_CUDA;
+  }
+  permutation_kernel<<<E, 1024, 0, stream>>>(top_idx, counts, offsets, dest_row, src_token, T * k, E, k, row_align);
   return check_launch("permutation_kernel");
 }
 

@@ -66,6 +66,27 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out.view(*x.shape[:-1], N)
 
 
+def linear_multi(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[x @ W0.T | x @ W1.T | ...] in one GEMM launch (up to 3 nn.Linear weights with equal out_features)."""
+    _chk(x)
+    K = x.shape[-1]
+    N = weights[0].shape[0]
+    x2 = x.reshape(-1, K)
+    M = x2.shape[0]
+    out = torch.empty((M, N * len(weights)), dtype=bf16, device=x.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = x2.data_ptr(), K, M, N, K
+    for s_, w in enumerate(weights):
+        _chk(w)
+        assert w.shape == weights[0].shape
+        d.b[s_] = w.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = len(weights), L.B_NK, 1
+    d.epilogue = L.EPI_LINEAR
+    d.out[0], d.ldo = out.data_ptr(), N * len(weights)
+    _run_gemm(d, x, "linear_multi")
+    return out
+
+
 def linear_swiglu(x: torch.Tensor, gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
     """silu(x @ gate_w.T) * (x @ up_w.T) in one GEMM (LlamaMLP front half, moe_lm.py:368-395)."""
     _chk(x), _chk(gate_w), _chk(up_w)
@@ -106,6 +127,105 @@ def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu
     d.dbg_lbo, d.dbg_sbo, d.dbg_kadv = dbg
     _run_gemm(d, a, "grouped_gemm")
     return out
+
+
+def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """Data-gradient of the grouped GEMM: out[rows of e] = a[rows of e] @ b[e].T with b [E, N_out, K] (K contiguous) —
+    i.e. the forward weight [E, in, out] used transposed, read in place (ARIA_B_GNK)."""
+    _chk(a), _chk(b), _chk(offsets, torch.int32)
+    rows, K = a.shape
+    E, N, Kb = b.shape
+    assert Kb == K and offsets.numel() == E + 1
+    out = torch.empty((rows, N), dtype=bf16, device=a.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = a.data_ptr(), a.stride(0), rows, N, K
+    d.b[0] = b.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GNK, E
+    d.group_offsets = offsets.data_ptr()
+    d.epilogue = L.EPI_LINEAR
+    d.out[0], d.ldo = out.data_ptr(), N
+    _run_gemm(d, a, "grouped_gemm_nt")
+    return out
+
+
+def matmul_kn(a: torch.Tensor, w_kn: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a [M, K] (row stride may exceed K) @ w_kn [K, N] (N contiguous) (+ residual): dense data-gradients, where the
+    nn.Linear weight [out, in] = [K, N] is consumed in place through the MN-major B path."""
+    if not (a.is_cuda and a.dtype == bf16 and a.stride(1) == 1 and a.data_ptr() % 16 == 0):
+        raise RuntimeError("matmul_kn: a must be CUDA bf16 with contiguous rows")
+    _chk(w_kn)
+    M, K = a.shape
+    Kw, N = w_kn.shape
+    assert K == Kw
+    out = torch.empty((M, N), dtype=bf16, device=a.device)
+    off = torch.tensor([0, M], dtype=torch.int32, device=a.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = a.data_ptr(), a.stride(0), M, N, K
+    d.b[0] = w_kn.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GKN, 1
+    d.group_offsets = off.data_ptr()
+    d.epilogue = L.EPI_LINEAR
+    if residual is not None:
+        d.residual, d.ldr = _chk(residual).data_ptr(), N
+    d.out[0], d.ldo = out.data_ptr(), N
+    _run_gemm(d, a, "matmul_kn")
+    return out
+
+
+def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """out[g] = a[rows of g].T @ b[rows of g]; a [rows, Md], b [rows, Nd] (row strides allowed), offsets [G+1] int32 with
+    16-aligned entries -> out [G, Md, Nd] bf16 (fp32 accumulation in TMEM)."""
+    for t in (a, b):
+        if not (t.is_cuda and t.dtype == bf16 and t.stride(1) == 1 and t.data_ptr() % 16 == 0):
+            raise RuntimeError("grouped_wgrad: operands must be CUDA bf16 with contiguous rows")
+    _chk(offsets, torch.int32)
+    rows, Md = a.shape
+    Nd = b.shape[1]
+    G = offsets.numel() - 1
+    out = torch.empty((G, Md, Nd), dtype=bf16, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(L.load().aria_grouped_wgrad(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), _p(offsets), rows, Md, Nd, G,
+                                            _stream(a)), "grouped_wgrad")
+    return out
+
+
+def swiglu_fwd(h1: torch.Tensor) -> torch.Tensor:
+    _chk(h1)
+    rows, I2 = h1.shape
+    h = torch.empty((rows, I2 // 2), dtype=bf16, device=h1.device)
+    with torch.cuda.device(h1.device):
+        L.check(L.load().aria_swiglu_fwd(_p(h1), _p(h), rows, I2 // 2, _stream(h1)), "swiglu_fwd")
+    return h
+
+
+def swiglu_bwd(h1: torch.Tensor, dh: torch.Tensor) -> torch.Tensor:
+    _chk(h1), _chk(dh)
+    rows, I2 = h1.shape
+    dh1 = torch.empty_like(h1)
+    with torch.cuda.device(h1.device):
+        L.check(L.load().aria_swiglu_bwd(_p(h1), _p(dh), _p(dh1), rows, I2 // 2, _stream(h1)), "swiglu_bwd")
+    return dh1
+
+
+def combine_bwd(dout: torch.Tensor, y: torch.Tensor, dest_row: torch.Tensor, scores: torch.Tensor):
+    """-> (dy [rows(y), d] bf16 with pad rows zero, dscores [T, k] fp32)."""
+    _chk(dout), _chk(y), _chk(dest_row, torch.int32), _chk(scores)
+    T, k = scores.shape
+    dy = torch.zeros_like(y)
+    ds = torch.empty((T, k), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        L.check(L.load().aria_combine_bwd(_p(dout), _p(y), _p(dest_row), _p(scores), _p(dy), _p(ds), T, y.shape[1], k,
+                                          _stream(y)), "combine_bwd")
+    return dy, ds
+
+
+def router_bwd(dscores: torch.Tensor, scores: torch.Tensor, top_idx: torch.Tensor, E: int) -> torch.Tensor:
+    _chk(dscores, torch.float32), _chk(scores), _chk(top_idx, torch.int32)
+    T, k = scores.shape
+    dl = torch.empty((T, E), dtype=bf16, device=scores.device)
+    with torch.cuda.device(scores.device):
+        L.check(L.load().aria_router_bwd(_p(dscores), _p(scores), _p(top_idx), _p(dl), T, E, k, _stream(scores)), "router_bwd")
+    return dl
 
 
 def qkv_heads(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
@@ -170,16 +290,18 @@ def route_from_logits(logits: torch.Tensor, k: int):
     return scores, idx, counts
 
 
-def build_permutation(top_idx: torch.Tensor, counts: torch.Tensor):
+def build_permutation(top_idx: torch.Tensor, counts: torch.Tensor, row_align: int = 1):
+    """row_align=16 (training): expert blocks start on multiples of 16 rows; `src` then has T*k + E*15 slots (upper bound
+    of the padded row count, the true total is offsets[E]) and pad rows carry -1."""
     _chk(top_idx, torch.int32), _chk(counts, torch.int32)
     T, k = top_idx.shape
     E = counts.numel()
     dev = top_idx.device
     offsets = torch.empty((E + 1,), dtype=torch.int32, device=dev)
     dest = torch.empty((T * k,), dtype=torch.int32, device=dev)
-    src = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    src = torch.empty((T * k + E * (row_align - 1),), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        L.check(L.load().aria_build_permutation(_p(top_idx), _p(counts), _p(offsets), _p(dest), _p(src), T, E, k,
+        L.check(L.load().aria_build_permutation(_p(top_idx), _p(counts), _p(offsets), _p(dest), _p(src), T, E, k, row_align,
                                                 _stream(top_idx)), "build_permutation")
     return offsets, dest, src
 

@@ -36,7 +36,8 @@ const char* aria_build_arch(void);
  * epilogues of the hot path.  Rounding points mirror the reference's op-by-op bf16 rounding.
  * ------------------------------------------------------------------------------------------------ */
 enum { ARIA_B_NK = 0,  /* B[n_seg][N,K], K contiguous — torch.nn.Linear.weight                        */
-       ARIA_B_GKN = 1  /* B[G,K,N],      N contiguous — GroupedGEMM.weight (moe_lm.py:465)            */ };
+       ARIA_B_GKN = 1, /* B[G,K,N],      N contiguous — GroupedGEMM.weight (moe_lm.py:465)            */
+       ARIA_B_GNK = 2  /* B[G,N,K],      K contiguous — the same expert weight used transposed (dgrad) */ };
 enum { ARIA_EPI_LINEAR = 0, /* out = act(acc + bias) (+ residual)                                      */
        ARIA_EPI_SWIGLU = 1, /* out = silu(acc_gate) * acc_up  (moe_lm.py:505-507 `glu`, LlamaMLP)      */
        ARIA_EPI_HEADS = 2   /* (+bias) (+RoPE) and scatter to [B, H, T, head_ld] head-major buffers    */ };
@@ -89,6 +90,12 @@ int aria_gemm(const aria_gemm_desc_t* desc, aria_stream_t stream);
 int aria_grouped_gemm(const void* a, const void* b, void* out, const int32_t* group_offsets, int64_t rows,
                       int64_t k, int64_t n, int32_t num_groups, aria_stream_t stream);
 
+/* Weight gradient of a (grouped) linear layer — backward of gmm / F.linear:
+ *   out[g, m, n] = sum_{r in group g} a[r, m] * b[r, n]   a [rows, md] (row stride lda), b [rows, nd] (ldb), out [G, md, nd] bf16.
+ * group_offsets[G+1]: device int32 row offsets, each a multiple of 16 (aria_build_permutation with row_align = 16). */
+int aria_grouped_wgrad(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, const int32_t* group_offsets,
+                       int64_t rows, int64_t md, int64_t nd, int32_t num_groups, aria_stream_t stream);
+
 /* int64 counts (tokens_per_expert as the reference passes it, moe_lm.py:264-269) -> int32 offsets[G+1]. */
 int aria_offsets_from_counts(const int64_t* counts, int32_t* offsets, int32_t num_groups, aria_stream_t stream);
 
@@ -110,8 +117,10 @@ int aria_route_from_logits(const void* logits, int32_t* top_idx, void* scores, i
  *   offsets [E+1] int32 (exclusive scan of counts), dest_row [T*k] int32 (row of flattened (token,slot) in
  *   the expert-sorted order == inverse of the reference's `sorted_indices`), src_token [T*k] int32 (token of
  *   each sorted row == sorted_indices // k).  Order inside an expert = ascending flattened index (stable). */
+/* row_align = 1: dense layout (inference).  row_align = 16 (training): every expert's block starts on a multiple of 16
+ * rows; src_token then needs T*k + E*(row_align-1) slots and pad rows carry -1 (permute_rows writes zeros for them). */
 int aria_build_permutation(const int32_t* top_idx, const int32_t* counts, int32_t* offsets, int32_t* dest_row,
-                           int32_t* src_token, int64_t T, int32_t E, int32_t k, aria_stream_t stream);
+                           int32_t* src_token, int64_t T, int32_t E, int32_t k, int32_t row_align, aria_stream_t stream);
 /*   permuted[r, :] = x[src_token[r], :]  (index_select, moe_lm.py:330) */
 int aria_permute_rows(const void* x, const int32_t* src_token, void* permuted, int64_t rows, int32_t d,
                       aria_stream_t stream);
@@ -119,6 +128,20 @@ int aria_permute_rows(const void* x, const int32_t* src_token, void* permuted, i
  *   out[t] = bf16( sum_j bf16(y[dest_row[t*k+j]] * scores[t,j]) ) (+ shared[t]) ; fp32 accumulate. */
 int aria_unpermute_combine(const void* y, const int32_t* dest_row, const void* scores, const void* shared,
                            void* out, int64_t T, int32_t d, int32_t k, aria_stream_t stream);
+
+/* ---- backward of the MoE block (BASELINE cfg 5; autograd through moe_lm.py:548-577) ---- */
+/* h = bf16(bf16(silu(g)) * u) with g = h1[:, :I], u = h1[:, I:]  (unfused `glu`, moe_lm.py:505-507; training keeps h1). */
+int aria_swiglu_fwd(const void* h1, void* h, int64_t rows, int32_t I, aria_stream_t stream);
+/* dh1 = [dh * u * silu'(g) | dh * silu(g)] */
+int aria_swiglu_bwd(const void* h1, const void* dh, void* dh1, int64_t rows, int32_t I, aria_stream_t stream);
+/* backward of aria_unpermute_combine w.r.t. y and scores:
+ *   dy[dest_row[t*k+j]] = bf16(scores[t,j] * dout[t]),  dscores[t,j] = <dout[t], y[dest_row[t*k+j]]> (fp32).
+ * dy rows that no (t,j) maps to (alignment pads) must be pre-zeroed by the caller. */
+int aria_combine_bwd(const void* dout, const void* y, const int32_t* dest_row, const void* scores, void* dy, float* dscores,
+                     int64_t T, int32_t d, int32_t k, aria_stream_t stream);
+/* backward of softmax-over-top-k (moe_lm.py:261-262): dlogits[t, idx[t,j]] = s_j * (g_j - sum_i s_i g_i), zeros elsewhere. */
+int aria_router_bwd(const float* dscores, const void* scores, const int32_t* top_idx, void* dlogits, int64_t T, int32_t E,
+                    int32_t k, aria_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Norms, RoPE table, embedding, patches

@@ -1,0 +1,86 @@
+"""GPU: MoE block forward+backward (BASELINE cfg 5 unit) against torch autograd through the oracle restatement.
+The oracle runs in fp32 on the bf16-rounded parameters/inputs; our gradients are bf16 with fp32 accumulation, so the
+tolerance is a relative L2 error of 2e-2 per gradient tensor (router-near-tie tokens excluded from dx)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def test_wgrad_kernel_ragged_groups():
+    from aria_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    counts = [32, 0, 80, 16, 48]          # multiples of 16, one empty group
+    rows = sum(counts)
+    a = torch.randn(rows + 7, 192, generator=g).bfloat16()   # trailing rows beyond the last group must be ignored
+    b = torch.randn(rows + 7, 320, generator=g).bfloat16()
+    off = torch.tensor([0] + torch.tensor(counts).cumsum(0).tolist(), dtype=torch.int32)
+    got = ops.grouped_wgrad(a.to(DEV), b.to(DEV), off.to(DEV))
+    for e in range(len(counts)):
+        lo, hi = int(off[e]), int(off[e + 1])
+        want = a[lo:hi].float().t() @ b[lo:hi].float()
+        if hi == lo:
+            assert float(got[e].abs().max()) == 0.0
+        else:
+            assert _rel_l2(got[e], want) <= 1e-2
+
+
+def test_grouped_gemm_nt_matches_transposed_weight():
+    from aria_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    counts = [16, 48, 0, 130]
+    rows = sum(counts)
+    a = torch.randn(rows, 256, generator=g).bfloat16()
+    w = (torch.randn(4, 128, 256, generator=g) * 0.05).bfloat16()   # [E, N_out, K]
+    off = torch.tensor([0] + torch.tensor(counts).cumsum(0).tolist(), dtype=torch.int32)
+    got = ops.grouped_gemm_nt(a.to(DEV), w.to(DEV), off.to(DEV))
+    for e in range(4):
+        lo, hi = int(off[e]), int(off[e + 1])
+        if hi > lo:
+            assert _rel_l2(got[lo:hi], a[lo:hi].float() @ w[e].float().t()) <= 1e-2
+
+
+@pytest.mark.parametrize("T,E,k,d,I", [(40, 8, 2, 256, 128), (300, 64, 6, 256, 128)])
+def test_moe_layer_forward_backward_vs_oracle_autograd(T, E, k, d, I):
+    from aria_b200 import moe_lm, moe_train
+    from oracle import aria_oracle as O
+    from oracle import configs as C
+    tc = dict(hidden_size=d, moe_num_experts=E, moe_topk=k, moe_intermediate_size=I, moe_num_shared_experts=2)
+    gen = torch.Generator().manual_seed(7)
+    sd = {n: v.bfloat16() for n, v in C.moe_layer_state(tc, gen).items()}
+    x = torch.randn(1, T, d, generator=gen).bfloat16()
+    gout = torch.randn(1, T, d, generator=gen).bfloat16()
+    # oracle: fp32 autograd on the same (bf16-rounded) values
+    sd32 = {n: v.float().requires_grad_(True) for n, v in sd.items()}
+    x32 = x.float().requires_grad_(True)
+    with torch.enable_grad():
+        want, parts = O.moe_layer(x32, sd32, k, return_parts=True)
+        want.backward(gout.float())
+    # ours
+    layer = moe_lm.MoELayer(moe_lm.AriaMoELMConfig(**tc), device=DEV)
+    layer.load_state_dict({n: v.to(DEV) for n, v in sd.items()}, strict=True)
+    for p_ in layer.parameters():
+        p_.requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.enable_grad():
+        got = moe_train.moe_layer_train(layer, xg)
+        got.backward(gout.to(DEV))
+    lg = parts["logits"].detach().float().sort(1, descending=True).values
+    safe = ((lg[:, k - 1] - lg[:, k]) / lg.abs().amax(1) > 2 ** -6)
+    assert int(safe.sum()) >= T // 2
+    assert _rel_l2(got.detach().view(T, d)[safe], want.detach().view(T, d)[safe]) <= 1e-2
+    assert _rel_l2(xg.grad.view(T, d)[safe], x32.grad.view(T, d)[safe]) <= 2e-2
+    names = {"router.weight": layer.router.weight, "experts.fc1.weight": layer.experts.fc1.weight,
+             "experts.fc2.weight": layer.experts.fc2.weight, "shared_experts.gate_proj.weight": layer.shared_experts.gate_proj.weight,
+             "shared_experts.up_proj.weight": layer.shared_experts.up_proj.weight,
+             "shared_experts.down_proj.weight": layer.shared_experts.down_proj.weight}
+    all_safe = bool(safe.all())
+    for n, p_ in names.items():
+        tol = 2e-2 if all_safe else 1.5e-1   # a flipped near-tie token moves a whole row of expert/router gradient
+        assert _rel_l2(p_.grad, sd32[n].grad) <= tol, n
