@@ -98,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int col = n_idx * BN;
               const int seg = col / p.N;
               const CUtensorMap* tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + grp * p.b_group_rows);
+              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + (p.group_mod ? grp % p.group_mod : grp) * p.b_group_rows);
             }
           }
           if (++stage == STAGES) {
@@ -334,7 +334,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     if (two_cta && !swiglu) box_rows = BN / 2;
     for (int s = 0; s < 3; ++s) {
       const void* ptr = s < nb ? d->b[s] : d->b[0];
-      const uint64_t b_rows = b_gnk ? static_cast<uint64_t>(d->num_groups) * d->n : d->n;
+      const uint64_t b_rows = b_gnk ? static_cast<uint64_t>(d->group_mod > 0 ? d->group_mod : d->num_groups) * d->n : d->n;
       rc = make_tmap_2d(&tmB[s], ptr, d->k, b_rows, d->k * 2, BK, box_rows);
       if (rc) return rc;
     }

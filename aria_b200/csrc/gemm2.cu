@@ -111,7 +111,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int col = n_idx * BN;
               const int seg = col / p.N;
               const CUtensorMap* tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-              tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + static_cast<int>(rank) * BH + grp * p.b_group_rows);
+              tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + static_cast<int>(rank) * BH + (p.group_mod ? grp % p.group_mod : grp) * p.b_group_rows);
             }
           }
           if (++stage == STAGES) {

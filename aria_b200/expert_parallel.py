@@ -10,8 +10,8 @@ each MoE layer does
     -> reverse all-to-all-v (combine) -> score-weighted sum + local shared expert
 
 over `torch.distributed` (NCCL on NVLink 5 / NVSwitch: uniform bandwidth, so a flat all-to-all).  The grouped GEMM takes
-the (source rank, local expert) groups directly (`group_mod`), so received rows are never re-sorted.  Forward only in
-this round; one 4*E-byte D2H of the counts per layer is needed because NCCL's all-to-all-v takes host split sizes.
+the (source rank, local expert) groups directly (`group_mod`), so received rows are never re-sorted.  Inference forward
+(`ExpertParallelMoE`) and training forward+backward (`ep_moe_layer_train`); one 4*E-byte D2H of the counts per layer is needed because NCCL's all-to-all-v takes host split sizes.
 
 Parity: the W-rank result equals the single-device `MoELayer` on each rank's tokens (tests/test_ep_gloo.py on CPU
 through the oracle backend, tests/test_gpu_ep.py on 2 GPUs).
@@ -113,3 +113,89 @@ class ExpertParallelMoE:
 def exchange_bytes_per_layer(tokens_per_rank: int, topk: int, hidden: int, world: int) -> float:
     """Expected bytes a rank sends per direction per layer: (W-1)/W of its k*T rows leave the rank."""
     return tokens_per_rank * topk * hidden * 2 * (world - 1) / world
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Training path (BASELINE cfg 5: expert-parallel forward + backward).  CUDA only.
+class _EPMoEFunction(torch.autograd.Function):
+    """Expert-parallel MoE layer with explicit backward.  Forward = the exchange above with the training-mode layout
+    (every expert block padded to a multiple of 16 rows on the SENDER, so the (source rank, expert) groups on the receiver
+    are 16-aligned and feed the ragged wgrad GEMM directly).  Backward mirrors it: grad rows take the same two all-to-alls
+    in reverse; expert weight grads stay on the owning rank (no all-reduce); router / shared-expert grads are per-rank
+    partial sums (the usual data-parallel all-reduce is left to the caller, as in the reference's DP/ZeRO setup)."""
+
+    @staticmethod
+    def forward(ctx, x, w_router, fc1, fc2, gate_w, up_w, down_w, topk, group):
+        from . import ops
+        W = dist.get_world_size(group)
+        E = w_router.shape[0]
+        E_loc = E // W
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        scores, idx, counts, _ = ops.router_topk(x2, w_router, topk)
+        offsets, dest, src = ops.build_permutation(idx, counts, row_align=16)
+        xp = ops.permute_rows(x2, src)
+        padded = ((counts.to(torch.int64) + 15) // 16) * 16           # rows sent per expert (incl. zero pads)
+        send_counts = padded.view(W, E_loc)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        send_host = send_counts.sum(1).tolist()
+        recv_host = recv_counts.sum(1).tolist()
+        n_send = sum(send_host)
+        xr = torch.empty((sum(recv_host), x2.shape[1]), dtype=x2.dtype, device=x2.device)
+        dist.all_to_all_single(xr, xp[:n_send], output_split_sizes=recv_host, input_split_sizes=send_host, group=group)
+        roff = ops.offsets_from_counts(recv_counts.reshape(-1).contiguous())
+        h1 = ops.grouped_gemm(xr, fc1, roff, group_mod=E_loc)
+        h = ops.swiglu_fwd(h1)
+        yr = ops.grouped_gemm(h, fc2, roff, group_mod=E_loc)
+        y = torch.zeros_like(xp)
+        dist.all_to_all_single(y[:n_send], yr, output_split_sizes=send_host, input_split_sizes=recv_host, group=group)
+        hs1 = ops.linear_multi(x2, [gate_w, up_w])
+        hs = ops.swiglu_fwd(hs1)
+        shared = ops.linear(hs, down_w)
+        out = ops.unpermute_combine(y, dest, scores, shared)
+        ctx.save_for_backward(x2, w_router, fc1, fc2, gate_w, up_w, down_w, scores, idx, dest, y, xr, h1, h, roff, hs1, hs)
+        ctx.meta = (shape, send_host, recv_host, n_send, E_loc, group, xp.shape[0])
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        (x2, w_router, fc1, fc2, gate_w, up_w, down_w, scores, idx, dest, y, xr, h1, h, roff, hs1, hs) = ctx.saved_tensors
+        shape, send_host, recv_host, n_send, E_loc, group, rows_pad = ctx.meta
+        E, d = w_router.shape
+        Is = gate_w.shape[0]
+        T = x2.shape[0]
+        do = dout.reshape(-1, d).contiguous()
+        dense = torch.tensor([0, T], dtype=torch.int32, device=do.device)
+        dy, dscores = ops.combine_bwd(do, y, dest, scores)
+        dyr = torch.empty_like(xr)
+        dist.all_to_all_single(dyr, dy[:n_send], output_split_sizes=recv_host, input_split_sizes=send_host, group=group)
+        # (source rank, expert) groups -> per-expert weight grads: sum the W partial grads of each local expert
+        W = len(send_host)
+        d_fc2 = ops.grouped_wgrad(h, dyr, roff).view(W, E_loc, h.shape[1], d).float().sum(0).to(fc2.dtype)
+        dh = ops.grouped_gemm_nt(dyr, fc2, roff, group_mod=E_loc)
+        dh1 = ops.swiglu_bwd(h1, dh)
+        d_fc1 = ops.grouped_wgrad(xr, dh1, roff).view(W, E_loc, d, h1.shape[1]).float().sum(0).to(fc1.dtype)
+        dxr = ops.grouped_gemm_nt(dh1, fc1, roff, group_mod=E_loc)
+        dxp = torch.zeros((rows_pad, d), dtype=dxr.dtype, device=dxr.device)
+        dist.all_to_all_single(dxp[:n_send], dxr, output_split_sizes=send_host, input_split_sizes=recv_host, group=group)
+        d_down = ops.grouped_wgrad(do, hs, dense)[0]
+        dhs = ops.matmul_kn(do, down_w)
+        dhs1 = ops.swiglu_bwd(hs1, dhs)
+        d_gate = ops.grouped_wgrad(dhs1[:, :Is], x2, dense)[0]
+        d_up = ops.grouped_wgrad(dhs1[:, Is:], x2, dense)[0]
+        dx = ops.matmul_kn(dhs1[:, :Is], gate_w)
+        dx = ops.matmul_kn(dhs1[:, Is:], up_w, residual=dx)
+        dlogits = ops.router_bwd(dscores, scores, idx, E)
+        d_router = ops.grouped_wgrad(dlogits, x2, dense)[0]
+        dx = ops.matmul_kn(dlogits, w_router, residual=dx)
+        dx = ops.unpermute_combine(dxp, dest, torch.ones_like(scores), dx)
+        return dx.view(shape), d_router, d_fc1, d_fc2, d_gate, d_up, d_down, None, None
+
+
+def ep_moe_layer_train(x, w: dict, topk: int, group=None):
+    """Differentiable expert-parallel MoE layer; `w` as in ExpertParallelMoE (expert weights = this rank's slice)."""
+    return _EPMoEFunction.apply(x, w["router.weight"], w["experts.fc1.weight"], w["experts.fc2.weight"],
+                                w["shared_experts.gate_proj.weight"], w["shared_experts.up_proj.weight"],
+                                w["shared_experts.down_proj.weight"], topk, group)

@@ -129,18 +129,20 @@ def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu
     return out
 
 
-def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, group_mod: int = 0) -> torch.Tensor:
     """Data-gradient of the grouped GEMM: out[rows of e] = a[rows of e] @ b[e].T with b [E, N_out, K] (K contiguous) —
     i.e. the forward weight [E, in, out] used transposed, read in place (ARIA_B_GNK)."""
     _chk(a), _chk(b), _chk(offsets, torch.int32)
     rows, K = a.shape
     E, N, Kb = b.shape
-    assert Kb == K and offsets.numel() == E + 1
+    G = offsets.numel() - 1
+    assert Kb == K and (G == E if not group_mod else (group_mod == E and G % E == 0))
     out = torch.empty((rows, N), dtype=bf16, device=a.device)
     d = L.GemmDesc()
     d.a, d.lda, d.m, d.n, d.k = a.data_ptr(), a.stride(0), rows, N, K
     d.b[0] = b.data_ptr()
-    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GNK, E
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GNK, G
+    d.group_mod = group_mod
     d.group_offsets = offsets.data_ptr()
     d.epilogue = L.EPI_LINEAR
     d.out[0], d.ldo = out.data_ptr(), N

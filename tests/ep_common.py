@@ -93,3 +93,62 @@ def ep_worker(rank, world, port, backend_name, device_kind, tc, T, dtype_name, r
                 "n_safe": int(safe.sum()), "n": int(safe.numel())}, os.path.join(result_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def ep_train_worker(rank, world, port, tc, T, result_dir):
+    """One rank: expert-parallel MoE forward+backward (CUDA/NCCL) vs fp32 autograd through the oracle on the CONCATENATED
+    batch of all ranks (expert weight grads sum over every rank's tokens)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import torch.distributed as dist
+    from aria_b200.expert_parallel import ExpertParallelMoE, ep_moe_layer_train
+    from oracle import aria_oracle as O
+    from oracle import configs as C
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    k, d, E = tc["moe_topk"], tc["hidden_size"], tc["moe_num_experts"]
+    gen = torch.Generator().manual_seed(1234)
+    full = {n: v.bfloat16() for n, v in C.moe_layer_state(tc, gen).items()}
+    xs, gs = [], []
+    for r in range(world):
+        xg = torch.Generator().manual_seed(100 + r)
+        xs.append(torch.randn(T + 3 * r, d, generator=xg).bfloat16())
+        gs.append(torch.randn(T + 3 * r, d, generator=xg).bfloat16())
+    # reference: fp32 autograd over all ranks' tokens
+    sd32 = {n: v.float().requires_grad_(True) for n, v in full.items()}
+    xall = torch.cat(xs).float().requires_grad_(True)
+    with torch.enable_grad():
+        want, parts = O.moe_layer(xall, sd32, k, return_parts=True)
+        want.backward(torch.cat(gs).float())
+    lo = sum(x.shape[0] for x in xs[:rank])
+    hi = lo + xs[rank].shape[0]
+    # ours
+    shard = {n: v.to(dev).requires_grad_(True) for n, v in ExpertParallelMoE.shard_state(full, rank, world).items()}
+    xr = xs[rank].to(dev).requires_grad_(True)
+    with torch.enable_grad():
+        got = ep_moe_layer_train(xr, shard, k)
+        got.backward(gs[rank].to(dev))
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        a, b = a.float().cpu(), b.float().cpu()
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+    lg = parts["logits"].detach().float().sort(1, descending=True).values
+    safe_all = (lg[:, k - 1] - lg[:, k]) / lg.abs().amax(1) > 2 ** -6
+    safe = safe_all[lo:hi]
+    E_loc = E // world
+    e0, e1 = rank * E_loc, (rank + 1) * E_loc
+    res = {"out": rel(got.detach()[safe], want.detach()[lo:hi][safe]), "dx": rel(xr.grad[safe], xall.grad[lo:hi][safe]),
+           "d_fc1": rel(shard["experts.fc1.weight"].grad, sd32["experts.fc1.weight"].grad[e0:e1]),
+           "d_fc2": rel(shard["experts.fc2.weight"].grad, sd32["experts.fc2.weight"].grad[e0:e1]),
+           "all_safe": bool(safe_all.all()), "n_safe": int(safe.sum()), "n": int(safe.numel())}
+    torch.save(res, os.path.join(result_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
