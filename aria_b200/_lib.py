@@ -50,7 +50,7 @@ SIGNATURES = {
     "aria_router_topk": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "aria_route_from_logits": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_build_permutation": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
-    "aria_grouped_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i64, i64, i64, i32, vp]),
+    "aria_grouped_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i64, i64, i64, i32, i32, vp]),
     "aria_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
     "aria_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "aria_combine_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),

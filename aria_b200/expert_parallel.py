@@ -171,12 +171,11 @@ class _EPMoEFunction(torch.autograd.Function):
         dy, dscores = ops.combine_bwd(do, y, dest, scores)
         dyr = torch.empty_like(xr)
         dist.all_to_all_single(dyr, dy[:n_send], output_split_sizes=recv_host, input_split_sizes=send_host, group=group)
-        # (source rank, expert) groups -> per-expert weight grads: sum the W partial grads of each local expert
         W = len(send_host)
-        d_fc2 = ops.grouped_wgrad(h, dyr, roff).view(W, E_loc, h.shape[1], d).float().sum(0).to(fc2.dtype)
+        d_fc2 = ops.grouped_wgrad(h, dyr, roff, num_sources=W)   # sums the W (source rank) row blocks of each local expert
         dh = ops.grouped_gemm_nt(dyr, fc2, roff, group_mod=E_loc)
         dh1 = ops.swiglu_bwd(h1, dh)
-        d_fc1 = ops.grouped_wgrad(xr, dh1, roff).view(W, E_loc, d, h1.shape[1]).float().sum(0).to(fc1.dtype)
+        d_fc1 = ops.grouped_wgrad(xr, dh1, roff, num_sources=W)
         dxr = ops.grouped_gemm_nt(dh1, fc1, roff, group_mod=E_loc)
         dxp = torch.zeros((rows_pad, d), dtype=dxr.dtype, device=dxr.device)
         dist.all_to_all_single(dxp[:n_send], dxr, output_split_sizes=send_host, input_split_sizes=recv_host, group=group)

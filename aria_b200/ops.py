@@ -174,20 +174,22 @@ def matmul_kn(a: torch.Tensor, w_kn: torch.Tensor, residual: Optional[torch.Tens
     return out
 
 
-def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, num_sources: int = 1) -> torch.Tensor:
     """out[g] = a[rows of g].T @ b[rows of g]; a [rows, Md], b [rows, Nd] (row strides allowed), offsets [G+1] int32 with
-    16-aligned entries -> out [G, Md, Nd] bf16 (fp32 accumulation in TMEM)."""
+    16-aligned entries -> out [G, Md, Nd] bf16 (fp32 accumulation in TMEM).  num_sources=S: offsets [S*G+1] over
+    (source, g) row groups, out[g] sums over the sources."""
     for t in (a, b):
         if not (t.is_cuda and t.dtype == bf16 and t.stride(1) == 1 and t.data_ptr() % 16 == 0):
             raise RuntimeError("grouped_wgrad: operands must be CUDA bf16 with contiguous rows")
     _chk(offsets, torch.int32)
     rows, Md = a.shape
     Nd = b.shape[1]
-    G = offsets.numel() - 1
+    G = (offsets.numel() - 1) // num_sources
+    assert G * num_sources + 1 == offsets.numel()
     out = torch.empty((G, Md, Nd), dtype=bf16, device=a.device)
     with torch.cuda.device(a.device):
         L.check(L.load().aria_grouped_wgrad(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), _p(offsets), rows, Md, Nd, G,
-                                            _stream(a)), "grouped_wgrad")
+                                            num_sources, _stream(a)), "grouped_wgrad")
     return out
 
 

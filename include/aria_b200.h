@@ -92,9 +92,11 @@ int aria_grouped_gemm(const void* a, const void* b, void* out, const int32_t* gr
 
 /* Weight gradient of a (grouped) linear layer — backward of gmm / F.linear:
  *   out[g, m, n] = sum_{r in group g} a[r, m] * b[r, n]   a [rows, md] (row stride lda), b [rows, nd] (ldb), out [G, md, nd] bf16.
- * group_offsets[G+1]: device int32 row offsets, each a multiple of 16 (aria_build_permutation with row_align = 16). */
+ * group_offsets: device int32 row offsets, each a multiple of 16 (aria_build_permutation with row_align = 16).
+ * num_sources = 1: offsets[G+1].  num_sources = S > 1 (expert parallelism): rows are grouped (source rank, g),
+ * source-major, offsets[S*G+1], and out[g] sums the S partial products — no separate reduction pass. */
 int aria_grouped_wgrad(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, const int32_t* group_offsets,
-                       int64_t rows, int64_t md, int64_t nd, int32_t num_groups, aria_stream_t stream);
+                       int64_t rows, int64_t md, int64_t nd, int32_t num_groups, int32_t num_sources, aria_stream_t stream);
 
 /* int64 counts (tokens_per_expert as the reference passes it, moe_lm.py:264-269) -> int32 offsets[G+1]. */
 int aria_offsets_from_counts(const int64_t* counts, int32_t* offsets, int32_t num_groups, aria_stream_t stream);

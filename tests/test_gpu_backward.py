@@ -84,3 +84,27 @@ def test_moe_layer_forward_backward_vs_oracle_autograd(T, E, k, d, I):
     for n, p_ in names.items():
         tol = 2e-2 if all_safe else 1.5e-1   # a flipped near-tie token moves a whole row of expert/router gradient
         assert _rel_l2(p_.grad, sd32[n].grad) <= tol, n
+
+
+def test_wgrad_two_cta_path_and_sources():
+    """Enough 256x256 output tiles to take the 2-CTA kernel (G*ceil(Md/256)*ceil(Nd/256) >= 74), plus the expert-parallel
+    `num_sources` accumulation (offsets over (source, group) pairs, out[g] sums the sources)."""
+    from aria_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    G, S, Md, Nd = 40, 2, 256, 512
+    counts = (torch.randint(0, 6, (S * G,), generator=g) * 16).tolist()   # multiples of 16, some empty
+    rows = sum(counts)
+    a = torch.randn(rows, Md, generator=g).bfloat16()
+    b = torch.randn(rows, Nd, generator=g).bfloat16()
+    off = torch.tensor([0] + torch.tensor(counts).cumsum(0).tolist(), dtype=torch.int32)
+    got = ops.grouped_wgrad(a.to(DEV), b.to(DEV), off.to(DEV), num_sources=S)
+    assert got.shape == (G, Md, Nd)
+    for e in range(0, G, 7):
+        want = torch.zeros(Md, Nd)
+        for s in range(S):
+            lo, hi = int(off[s * G + e]), int(off[s * G + e + 1])
+            want += a[lo:hi].float().t() @ b[lo:hi].float()
+        if float(want.abs().max()) == 0:
+            assert float(got[e].abs().max()) == 0.0
+        else:
+            assert _rel_l2(got[e], want) <= 1e-2
