@@ -64,6 +64,14 @@ SIGNATURES = {
     "aria_merge_image_features": (i32, [vp, i64, vp, vp, vp, i64, i32, vp]),
     "aria_im2col_patches": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "aria_add_pos_embedding": (i32, [vp, vp, vp, vp, i64, i32, vp]),
+    "aria_enable_peer_access": (i32, [i32]),
+    "aria_ipc_export": (i32, [vp, vp, vp]),
+    "aria_ipc_open": (i32, [vp, vp]),
+    "aria_ipc_close": (i32, [vp]),
+    "aria_ep_publish_counts": (i32, [vp, vp, i32, i32, i32, vp]),
+    "aria_peer_barrier": (i32, [vp, i32, i32, i32, vp]),
+    "aria_ep_layout": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
+    "aria_scatter_rows_grouped": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, i64, vp]),
     "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),
     "aria_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i64, vp]),
     "aria_attention_decode_workspace_bytes": (i64, [i32, i32, i32]),

@@ -1,4 +1,6 @@
 // Row-wise / gather kernels around the GEMMs (all HBM-bound, 128-bit accesses, one warp per row).
+#include <string.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -322,4 +324,64 @@ extern "C" int aria_add_pos_embedding(const void* x, const int64_t* pos_ids, con
   add_pos_kernel<<<rows_grid(rows, 8), 256, 0, stream>>>(static_cast<const uint4*>(x), pos_ids, static_cast<const uint4*>(table),
                                                          static_cast<uint4*>(out), rows, d / 8);
   return check_launch("add_pos_kernel");
+}
+
+// Lets kernels launched on the current device load/store memory of `peer_device` (NVLink P2P); idempotent.
+extern "C" int aria_enable_peer_access(int32_t peer_device) {
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) return ARIA_ERR_CUDA;
+  if (cur == peer_device) return ARIA_OK;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can) return ARIA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return ARIA_OK;
+  }
+  return e == cudaSuccess ? ARIA_OK : ARIA_ERR_CUDA;
+}
+
+// CUDA IPC plumbing for peer-mapped buffers (one arena per rank).  export: handle of the cudaMalloc allocation that
+// contains `ptr` + byte offset of `ptr` inside it.  open: maps a peer's allocation into the CURRENT device's context with
+// lazy peer access, so that kernels on this GPU can load/store it over NVLink.
+extern "C" int aria_ipc_export(const void* ptr, void* handle64, int64_t* offset_out) {
+  ARIA_CHECK_ARG(ptr && handle64 && offset_out);
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)) != cudaSuccess) {
+    fprintf(stderr, "aria_b200: cudaIpcGetMemHandle failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return ARIA_ERR_CUDA;
+  }
+  memcpy(handle64, &h, sizeof(h));
+  typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static PFN_range fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return ARIA_ERR_CUDA;
+    fn = reinterpret_cast<PFN_range>(p);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return ARIA_ERR_CUDA;
+  *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return ARIA_OK;
+}
+
+extern "C" int aria_ipc_open(const void* handle64, void** base_out) {
+  ARIA_CHECK_ARG(handle64 && base_out);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "aria_b200: cudaIpcOpenMemHandle failed: %s\n", cudaGetErrorString(e));
+    cudaGetLastError();
+    return ARIA_ERR_CUDA;
+  }
+  *base_out = p;
+  return ARIA_OK;
+}
+
+extern "C" int aria_ipc_close(void* base) {
+  return cudaIpcCloseMemHandle(base) == cudaSuccess ? ARIA_OK : ARIA_ERR_CUDA;
 }

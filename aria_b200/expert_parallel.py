@@ -59,7 +59,10 @@ class ExpertParallelMoE:
     weights: dict with the reference parameter names; `experts.fc1.weight` / `experts.fc2.weight` hold ONLY this rank's
     slice [E/W, ...]; router and shared-expert weights are replicated."""
 
-    def __init__(self, weights: dict, num_experts: int, topk: int, group=None, backend=None):
+    def __init__(self, weights: dict, num_experts: int, topk: int, group=None, backend=None, transport=None):
+        """transport: a `PeerTransport` -> the exchange runs over NVLink peer memory with our own kernels (fused
+        permute+dispatch, device-side barriers, no host sync); None -> NCCL all-to-all-v (needs one host sync)."""
+        self.transport = transport
         self.w = weights
         self.E = num_experts
         self.k = topk
@@ -82,6 +85,8 @@ class ExpertParallelMoE:
         return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.transport is not None:
+            return _ep_forward_p2p(self, x)
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         be, W, E_loc = self.backend, self.W, self.E_loc
@@ -108,6 +113,89 @@ class ExpertParallelMoE:
         return be.combine(y, dest, scores, shared).view(shape)
 
     __call__ = forward
+
+
+class PeerTransport:
+    """NVLink peer-memory transport for the expert-parallel exchange (no NCCL, no host sync, CUDA-graph friendly).
+    One arena per rank, mapped by every peer (aria_b200/peer.py):
+
+        counts_all [W, E] int32 | flags [W] int32 | recv_x [cap_rows, d] bf16 | ret_y [T_max*k, d] bf16
+
+    cap_rows = W * T_max * k covers the worst case of every token of every rank routed to one rank's experts."""
+
+    def __init__(self, T_max: int, hidden: int, num_experts: int, topk: int, device, group=None):
+        from .peer import PeerArena
+        self.group = group
+        self.W = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.E, self.k, self.d = num_experts, topk, hidden
+        self.E_loc = num_experts // self.W
+        self.cap_rows = self.W * T_max * topk
+        self.ret_rows = T_max * topk
+        al = lambda n: (n + 1023) // 1024 * 1024
+        self.off_counts = 0
+        self.off_flags = al(self.W * num_experts * 4)
+        self.off_recv = self.off_flags + al(self.W * 4)
+        self.off_ret = self.off_recv + al(self.cap_rows * hidden * 2)
+        total = self.off_ret + al(self.ret_rows * hidden * 2)
+        self.arena = PeerArena(total, device, group)
+        dev = torch.device(device)
+        mk = lambda off: torch.tensor([self.arena.ptr(r, off) for r in range(self.W)], dtype=torch.int64, device=dev)
+        self.p_counts, self.p_flags, self.p_recv, self.p_ret = mk(self.off_counts), mk(self.off_flags), mk(self.off_recv), mk(self.off_ret)
+        self.counts_all = self.arena.local_view(self.off_counts, (self.W, num_experts), torch.int32)
+        self.recv_x = self.arena.local_view(self.off_recv, (self.cap_rows, hidden), torch.bfloat16)
+        self.ret_y = self.arena.local_view(self.off_ret, (self.ret_rows, hidden), torch.bfloat16)
+        self.roff = torch.zeros(self.W * self.E_loc + 1, dtype=torch.int32, device=dev)
+        self.send_base = torch.zeros(num_experts, dtype=torch.int32, device=dev)
+        self.ret_base = torch.zeros(self.W * self.E_loc, dtype=torch.int32, device=dev)
+        self.epoch = 0
+        self.device = dev
+
+    def barrier(self):
+        from . import _lib as L
+        import ctypes as C
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            L.check(L.load().aria_peer_barrier(C.c_void_p(self.p_flags.data_ptr()), self.rank, self.W, self.epoch,
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "peer_barrier")
+
+
+def _ep_forward_p2p(self, x: torch.Tensor) -> torch.Tensor:
+    """ExpertParallelMoE.forward over NVLink peer memory: the permute kernel stores each expert-sorted row directly into the
+    owning rank's receive buffer (fused permute + dispatch), and expert outputs are stored straight back into the source
+    rank's buffer at their sorted position; three device-side barriers per layer, zero host syncs."""
+    import ctypes as C
+    from . import _lib as L
+    from . import ops
+    tr = self.transport
+    lib = L.load()
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1]).contiguous()
+    T = x2.shape[0]
+    assert T * self.k <= tr.ret_rows, "PeerTransport was sized for fewer tokens"
+    stream = lambda: C.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    scores, idx, counts, _ = ops.router_topk(x2, self.w["router.weight"], self.k)
+    offsets, dest, src = ops.build_permutation(idx, counts)
+    with torch.cuda.device(x2.device):
+        L.check(lib.aria_ep_publish_counts(vp(counts), vp(tr.p_counts), tr.rank, tr.W, tr.E, stream()), "ep_publish_counts")
+        tr.barrier()
+        L.check(lib.aria_ep_layout(vp(tr.counts_all), tr.rank, tr.W, tr.E, vp(tr.roff), vp(tr.send_base), vp(tr.ret_base),
+                                   stream()), "ep_layout")
+        # fused permute + dispatch: expert-sorted token rows -> the owners' receive buffers, over NVLink
+        L.check(lib.aria_scatter_rows_grouped(vp(x2), vp(src), vp(offsets), tr.E, vp(tr.send_base), tr.E_loc, vp(tr.p_recv),
+                                              tr.d, T * self.k, stream()), "scatter_rows_grouped")
+        # local shared expert while the rows are in flight on the other GPUs
+        shared = ops.linear(ops.linear_swiglu(x2, self.w["shared_experts.gate_proj.weight"],
+                                              self.w["shared_experts.up_proj.weight"]), self.w["shared_experts.down_proj.weight"])
+        tr.barrier()
+        h = ops.grouped_gemm(tr.recv_x, self.w["experts.fc1.weight"], tr.roff, swiglu=True, group_mod=tr.E_loc)
+        y_recv = ops.grouped_gemm(h, self.w["experts.fc2.weight"], tr.roff, group_mod=tr.E_loc)
+        # way back: expert outputs -> the source ranks' buffers at their original sorted rows
+        L.check(lib.aria_scatter_rows_grouped(vp(y_recv), None, vp(tr.roff), tr.W * tr.E_loc, vp(tr.ret_base), tr.E_loc,
+                                              vp(tr.p_ret), tr.d, tr.cap_rows, stream()), "scatter_rows_grouped")
+        tr.barrier()
+    return ops.unpermute_combine(tr.ret_y, dest, scores, shared).view(shape)
 
 
 def exchange_bytes_per_layer(tokens_per_rank: int, topk: int, hidden: int, world: int) -> float:

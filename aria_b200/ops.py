@@ -319,6 +319,15 @@ def permute_rows(x: torch.Tensor, src_token: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def permute_rows_to_ptr(x: torch.Tensor, src_token: torch.Tensor, out_ptr: int) -> None:
+    """permute_rows writing to a raw device address — e.g. a PEER GPU's arena (aria_b200.peer.PeerArena): the row copy
+    kernel then stores over NVLink."""
+    _chk(x), _chk(src_token, torch.int32)
+    with torch.cuda.device(x.device):
+        L.check(L.load().aria_permute_rows(_p(x), _p(src_token), C.c_void_p(out_ptr), src_token.numel(), x.shape[1], _stream(x)),
+                "permute_rows")
+
+
 def unpermute_combine(y: torch.Tensor, dest_row: torch.Tensor, scores: torch.Tensor,
                       shared: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(y), _chk(dest_row, torch.int32), _chk(scores)

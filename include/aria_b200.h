@@ -171,6 +171,28 @@ int aria_im2col_patches(const void* pixels, void* patches, int32_t B, int32_t S,
 int aria_add_pos_embedding(const void* x, const int64_t* pos_ids, const void* table, void* out, int64_t rows,
                            int32_t d, aria_stream_t stream);
 
+/* Multi-GPU: allow kernels on the current device to load/store `peer_device`'s memory over NVLink (idempotent). */
+int aria_enable_peer_access(int32_t peer_device);
+/* CUDA IPC for peer-mapped arenas: export the 64-byte handle of the allocation containing `ptr` (+ byte offset of ptr in
+ * it); open maps a peer's allocation into the current device's context (lazy peer access) and returns its base. */
+int aria_ipc_export(const void* ptr, void* handle64, int64_t* offset_out);
+int aria_ipc_open(const void* handle64, void** base_out);
+int aria_ipc_close(void* base);
+
+/* Expert-parallel exchange over NVLink peer memory (aria_b200/csrc/ep.cu): replaces the all-to-all the reference's
+ * dispatcher lost (moe_lm.py:296-297).  `peer_*` arrays are device arrays of W addresses (one per rank, as mapped on THIS
+ * GPU).  All calls are asynchronous and need no host sync. */
+int aria_ep_publish_counts(const int32_t* counts, const uint64_t* peer_counts, int32_t rank, int32_t W, int32_t E,
+                           aria_stream_t stream);                      /* my counts[E] -> counts_all[rank][:] on every rank */
+int aria_peer_barrier(const uint64_t* peer_flags, int32_t rank, int32_t W, int32_t epoch, aria_stream_t stream);
+int aria_ep_layout(const int32_t* counts_all, int32_t rank, int32_t W, int32_t E, int32_t* roff, int32_t* send_base,
+                   int32_t* ret_base, aria_stream_t stream);          /* roff[W*E/W+1], send_base[E], ret_base[W*E/W] */
+/* Fused permute + dispatch (and the way back): row i of group g -> rank g/group_div, row dst_row_base[g] + i - off[g];
+ * source row = rows[src_token ? src_token[i] : i].  max_rows only sizes the grid. */
+int aria_scatter_rows_grouped(const void* rows, const int32_t* src_token, const int32_t* group_offsets, int32_t G,
+                              const int32_t* dst_row_base, int32_t group_div, const uint64_t* peer_bufs, int32_t d,
+                              int64_t max_rows, aria_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Attention (tcgen05 QK^T / PV, fp32 online softmax)
  * ------------------------------------------------------------------------------------------------ */

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
-from aria_b200.expert_parallel import ExpertParallelMoE, exchange_bytes_per_layer
+from aria_b200.expert_parallel import ExpertParallelMoE, PeerTransport, exchange_bytes_per_layer
 from aria_b200 import moe_lm
 
 rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0)); W = int(os.environ.get("WORLD_SIZE", 1))
@@ -25,7 +25,9 @@ w = {"router.weight": rnd(E, d), "experts.fc1.weight": rnd(E // W, d, 2 * I), "e
      "shared_experts.down_proj.weight": rnd(d, 2 * I)}
 gx = torch.Generator(device=dev).manual_seed(100 + rank)
 x = torch.randn(T, d, generator=gx, device=dev).bfloat16()
-ep = ExpertParallelMoE(w, E, k)
+mode = os.environ.get("EP_TRANSPORT", "nccl")
+transport = PeerTransport(T, d, E, k, dev) if mode == "p2p" else None
+ep = ExpertParallelMoE(w, E, k, transport=transport)
 for _ in range(3): ep(x)
 dist.barrier(); torch.cuda.synchronize()
 n = 10
@@ -37,7 +39,7 @@ ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     flops = T * 204.8e6  # per rank, balanced
-    print(json.dumps({"bench": "ep_moe_layer_forward", "world": W, "tokens_per_rank": T, "ms_per_layer": float(ms),
+    print(json.dumps({"bench": "ep_moe_layer_forward", "transport": mode, "world": W, "tokens_per_rank": T, "ms_per_layer": float(ms),
                       "tokens_per_s_all_ranks": W * T / float(ms) * 1e3, "tflops_per_rank": flops / float(ms) / 1e9,
                       "a2a_bytes_per_direction": exchange_bytes_per_layer(T, k, d, W)}))
 dist.destroy_process_group()

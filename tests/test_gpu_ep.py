@@ -12,11 +12,12 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("transport", ["cuda", "p2p"])   # NCCL all-to-all-v / our NVLink peer-memory kernels
 @pytest.mark.parametrize("E,k,T,d,I", [(8, 2, 50, 256, 128), (64, 6, 1024, 2560, 1664)])
-def test_ep_forward_two_gpus(E, k, T, d, I):
+def test_ep_forward_two_gpus(E, k, T, d, I, transport):
     tc = dict(hidden_size=d, moe_num_experts=E, moe_topk=k, moe_intermediate_size=I, moe_num_shared_experts=2)
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(ep_worker, args=(2, free_port(), "cuda", "cuda", tc, T, "bfloat16", tmp), nprocs=2, join=True)
+        mp.spawn(ep_worker, args=(2, free_port(), transport, "cuda", tc, T, "bfloat16", tmp), nprocs=2, join=True)
         for r in range(2):
             res = torch.load(f"{tmp}/rank{r}.pt")
             assert res["err_safe"] <= 1e-2 and res["n_safe"] >= res["n"] // 4, res
