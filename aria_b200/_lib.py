@@ -69,7 +69,7 @@ SIGNATURES = {
     "aria_ipc_open": (i32, [vp, vp]),
     "aria_ipc_close": (i32, [vp]),
     "aria_ep_publish_counts": (i32, [vp, vp, i32, i32, i32, vp]),
-    "aria_peer_barrier": (i32, [vp, i32, i32, i32, vp]),
+    "aria_peer_barrier": (i32, [vp, i32, i32, vp, vp]),
     "aria_ep_layout": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
     "aria_scatter_rows_grouped": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, i64, vp]),
     "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),

@@ -23,7 +23,13 @@ __global__ void ep_publish_counts_kernel(const int32_t* __restrict__ counts, con
   reinterpret_cast<int32_t*>(peer_counts[p])[rank * E + e] = counts[e];
 }
 
-__global__ void peer_barrier_kernel(const uint64_t* __restrict__ peer_flags, int rank, int W, int epoch) {
+// The epoch lives in device memory and is advanced by the kernel itself, so a CUDA graph that captured the barrier replays
+// correctly (every rank executes the same sequence of barriers, so the counters stay in step).
+__global__ void peer_barrier_kernel(const uint64_t* __restrict__ peer_flags, int rank, int W, int32_t* __restrict__ epoch_dev) {
+  __shared__ int s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++(*epoch_dev);
+  __syncthreads();
+  const int epoch = s_epoch;
   const int s = threadIdx.x;
   if (s >= W) return;
   __threadfence_system();  // everything this GPU stored before the barrier is visible before the flag
@@ -110,10 +116,10 @@ extern "C" int aria_ep_publish_counts(const int32_t* counts, const uint64_t* pee
   return check_launch("ep_publish_counts_kernel");
 }
 
-extern "C" int aria_peer_barrier(const uint64_t* peer_flags, int32_t rank, int32_t W, int32_t epoch, aria_stream_t stream_) {
+extern "C" int aria_peer_barrier(const uint64_t* peer_flags, int32_t rank, int32_t W, int32_t* epoch_dev, aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ARIA_CHECK_ARG(peer_flags && W >= 1 && W <= 32 && rank >= 0 && rank < W);
-  peer_barrier_kernel<<<1, 32, 0, stream>>>(peer_flags, rank, W, epoch);
+  ARIA_CHECK_ARG(peer_flags && epoch_dev && W >= 1 && W <= 32 && rank >= 0 && rank < W);
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(peer_flags, rank, W, epoch_dev);
   return check_launch("peer_barrier_kernel");
 }
 

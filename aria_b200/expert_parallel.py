@@ -148,15 +148,15 @@ class PeerTransport:
         self.roff = torch.zeros(self.W * self.E_loc + 1, dtype=torch.int32, device=dev)
         self.send_base = torch.zeros(num_experts, dtype=torch.int32, device=dev)
         self.ret_base = torch.zeros(self.W * self.E_loc, dtype=torch.int32, device=dev)
-        self.epoch = 0
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)  # device-side barrier counter (graph-replay safe)
         self.device = dev
 
     def barrier(self):
         from . import _lib as L
         import ctypes as C
-        self.epoch += 1
         with torch.cuda.device(self.device):
-            L.check(L.load().aria_peer_barrier(C.c_void_p(self.p_flags.data_ptr()), self.rank, self.W, self.epoch,
+            L.check(L.load().aria_peer_barrier(C.c_void_p(self.p_flags.data_ptr()), self.rank, self.W,
+                                               C.c_void_p(self.epoch.data_ptr()),
                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "peer_barrier")
 
 

@@ -61,6 +61,27 @@ class AriaForConditionalGeneration(nn.Module):
     def get_input_embeddings(self):
         return self.language_model.model.embed_tokens
 
+    def enable_expert_parallel(self, max_tokens: int, group=None):
+        """Shard the routed experts of every MoE layer over the ranks of `group` (rank r serves experts
+        [r*E/W, (r+1)*E/W), a dim-0 view of the HF weights) and exchange token rows over NVLink peer memory
+        (aria_b200.expert_parallel.PeerTransport).  Every rank must then call forward() in lock-step with its own tokens."""
+        import torch.distributed as dist
+        from .expert_parallel import ExpertParallelMoE, PeerTransport
+        t = self.config.text_config
+        W, r = dist.get_world_size(group), dist.get_rank(group)
+        tr = PeerTransport(max_tokens, t.hidden_size, t.moe_num_experts, t.moe_topk, self.device, group)
+        lo, hi = r * t.moe_num_experts // W, (r + 1) * t.moe_num_experts // W
+        for layer in self.language_model.model.layers:
+            m = layer.mlp
+            w = {"router.weight": m.router.weight, "experts.fc1.weight": m.experts.fc1.weight[lo:hi],
+                 "experts.fc2.weight": m.experts.fc2.weight[lo:hi],
+                 "shared_experts.gate_proj.weight": m.shared_experts.gate_proj.weight,
+                 "shared_experts.up_proj.weight": m.shared_experts.up_proj.weight,
+                 "shared_experts.down_proj.weight": m.shared_experts.down_proj.weight}
+            m.expert_parallel = ExpertParallelMoE(w, t.moe_num_experts, t.moe_topk, group=group, transport=tr)
+        self._ep_transport = tr
+        return tr
+
     @property
     def device(self):
         return self.language_model.lm_head.weight.device

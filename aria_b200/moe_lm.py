@@ -196,8 +196,11 @@ class MoELayer(nn.Module):
         self.token_dispatcher = TokenDispatcher(config)
         self.experts = GroupedMLP(config, device)
         self.shared_experts = SharedExpertMLP(config, device)
+        self.expert_parallel = None  # set by AriaForConditionalGeneration.enable_expert_parallel()
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        if self.expert_parallel is not None:
+            return self.expert_parallel(hidden_states)
         scores, indices, tokens_per_expert = self.router(hidden_states)
         permuted_tokens = self.token_dispatcher.token_permutation(hidden_states, indices, tokens_per_expert)
         expert_output = self.experts(permuted_tokens, self.token_dispatcher.expert_offsets)

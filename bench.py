@@ -194,6 +194,12 @@ def run_aria(args, rank, local_rank, world):
     model = AriaForConditionalGeneration(AriaConfig.from_dict(cfg), device=dev)
     init_random_(model, seed=0)
     n_params = sum(p.numel() for p in model.parameters())
+    # N > 1: every rank prefills its own request (data parallel).  ARIA_BENCH_MULTI=ep additionally shards the routed
+    # experts over the ranks (token rows exchanged by our NVLink peer-memory kernels): each GPU then streams 1/N of the
+    # expert weights per layer.  Default "replicas": N independent model replicas, no data-path collective.
+    multi = os.environ.get("ARIA_BENCH_MULTI", "replicas") if world > 1 else "single"
+    if multi == "ep":
+        model.enable_expert_parallel(T_TOTAL)
 
     g = torch.Generator().manual_seed(1234 + rank)
     pv_host = torch.randn(1, 3, 980, 980, generator=g).bfloat16().pin_memory()
@@ -206,15 +212,15 @@ def run_aria(args, rank, local_rank, world):
     rec = {"on": False, "ev": []}
     orig_gg = ops.grouped_gemm
 
-    def timed_gg(a, b, off, swiglu=False, dbg=(0, 0, 0)):
+    def timed_gg(a, b, off, swiglu=False, **kw):
         if rec["on"] and swiglu:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            y = orig_gg(a, b, off, swiglu=swiglu, dbg=dbg)
+            y = orig_gg(a, b, off, swiglu=swiglu, **kw)
             e1.record()
             rec["ev"].append((e0, e1, a.shape[0]))
             return y
-        return orig_gg(a, b, off, swiglu=swiglu, dbg=dbg)
+        return orig_gg(a, b, off, swiglu=swiglu, **kw)
 
     ops.grouped_gemm = timed_gg
 
@@ -294,6 +300,9 @@ def run_aria(args, rank, local_rank, world):
     peaks, peak_src = _peaks()
     tc = cfg["text_config"]
     E, d, I = tc["moe_num_experts"], tc["hidden_size"], tc["moe_intermediate_size"]
+    if multi == "ep":  # each rank streams its E/world experts; rows = this rank's share of all ranks' (token, slot) pairs
+        E = E // world
+        fc1_rows = T_TOTAL * tc["moe_topk"]
     fc1_bytes = E * d * 2 * I * 2 + fc1_rows * d * 2 + fc1_rows * I * 2  # weights + A read + out write
     fc1_avg = statistics.mean(fc1_ms) if fc1_ms else float("nan")
     achieved = fc1_bytes / (fc1_avg * 1e-3) / 1e9
@@ -312,7 +321,8 @@ def run_aria(args, rank, local_rank, world):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world, "seq_len": T_TOTAL,
-                       "parallelism": f"replicas x{world} (no data-path collective)", "params": n_params,
+                       "parallelism": (f"dp{world} + experts sharded ep{world} (NVLink peer-memory token exchange)" if multi == "ep"
+                                       else f"replicas x{world} (no data-path collective)"), "params": n_params,
                        "l2": "per-step working set = 50.6 GB of weights >> 126 MB L2, no flush needed"},
             "e2e": {"value": world * T_TOTAL / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": pv_host.numel() * 2 + ids_host.numel() * 8,

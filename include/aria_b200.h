@@ -184,7 +184,8 @@ int aria_ipc_close(void* base);
  * GPU).  All calls are asynchronous and need no host sync. */
 int aria_ep_publish_counts(const int32_t* counts, const uint64_t* peer_counts, int32_t rank, int32_t W, int32_t E,
                            aria_stream_t stream);                      /* my counts[E] -> counts_all[rank][:] on every rank */
-int aria_peer_barrier(const uint64_t* peer_flags, int32_t rank, int32_t W, int32_t epoch, aria_stream_t stream);
+int aria_peer_barrier(const uint64_t* peer_flags, int32_t rank, int32_t W, int32_t* epoch_dev /* device counter, advanced by the call */,
+                      aria_stream_t stream);
 int aria_ep_layout(const int32_t* counts_all, int32_t rank, int32_t W, int32_t E, int32_t* roff, int32_t* send_base,
                    int32_t* ret_base, aria_stream_t stream);          /* roff[W*E/W+1], send_base[E], ret_base[W*E/W] */
 /* Fused permute + dispatch (and the way back): row i of group g -> rank g/group_div, row dst_row_base[g] + i - off[g];

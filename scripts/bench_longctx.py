@@ -10,13 +10,20 @@ from oracle import configs as C
 torch.set_grad_enabled(False)
 dev = torch.device("cuda", 0)
 T = int(os.environ.get("T", 65536)); layers = int(os.environ.get("LM_LAYERS", 28))
-cfg = C.with_layers(C.ARIA_25B, layers, 1)
+cfg = C.with_layers(C.ARIA_25B, layers, int(os.environ.get("VIT_LAYERS", 1)))
 model = AriaForConditionalGeneration(AriaConfig.from_dict(cfg), device=dev)
 init_random_(model, 0)
+frames = int(os.environ.get("VIT_FRAMES", 0))
 ids = torch.randint(10, 100352, (1, T), device=dev)
+pv = None
+if frames:  # cfg 4 proper: `frames` synthetic 980-px frames -> 256 image tokens each, the rest random text
+    if model.vision_tower.config.num_hidden_layers == 1:
+        pass
+    ids[0, 64:64 + 256 * frames] = cfg["image_token_index"]
+    pv = torch.randn(frames, 3, 980, 980, device=dev).bfloat16()
 ids_h = ids.cpu()
 def fwd():
-    return model(ids, num_logits_to_keep=1, input_ids_host=ids_h).logits
+    return model(ids, pv, None, num_logits_to_keep=1, input_ids_host=ids_h).logits
 fwd(); torch.cuda.synchronize()
 events = []
 names = ["grouped_gemm", "attention", "linear", "linear_swiglu", "qkv_heads", "router_topk", "build_permutation", "permute_rows",
@@ -37,7 +44,7 @@ for n, x, y in events:
     c = agg.setdefault(n, [0, 0.0]); c[0] += 1; c[1] += x.elapsed_time(y)
 attn_fl = layers * 5120 * T * T
 moe_fl = layers * T * 153.35e6
-res = {"bench": "longctx_prefill", "T": T, "layers": layers, "ms": ms, "tokens_per_s": T / ms * 1e3,
+res = {"bench": "longctx_prefill", "T": T, "layers": layers, "vit_frames": frames, "ms": ms, "tokens_per_s": T / ms * 1e3,
        "finite": bool(torch.isfinite(out.float()).all()), "mem_GB": torch.cuda.max_memory_allocated() / 1e9,
        "ops_ms": {k: round(v[1], 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
        "attention_TFLOPs": attn_fl / agg["attention"][1] / 1e9,

@@ -32,6 +32,30 @@ elif mode in ("fc1", "fc2"):
         a = torch.randn(rows, I, device=dev).bfloat16()
         for _ in range(3):
             ops.grouped_gemm(a, w, off)
+elif mode in ("fc1_big", "wgrad_big"):
+    E, d, I, T = 64, 2560, 1664, 8192
+    rows = T * 6
+    off = torch.arange(0, rows + 1, rows // E, dtype=torch.int32, device=dev)
+    a = torch.randn(rows, d, device=dev).bfloat16()
+    if mode == "fc1_big":
+        w = (torch.randn(E, d, 2 * I, device=dev) * 0.02).bfloat16()
+        for _ in range(3):
+            ops.grouped_gemm(a, w, off, swiglu=True)
+    else:
+        g = torch.randn(rows, 2 * I, device=dev).bfloat16()
+        for _ in range(3):
+            ops.grouped_wgrad(a, g, off)
+elif mode == "small":
+    T, d, E, k = 8192, 2560, 64, 6
+    x = torch.randn(T, d, device=dev).bfloat16()
+    w = torch.ones(d, device=dev).bfloat16()
+    logits = torch.randn(T, E, device=dev).bfloat16()
+    for _ in range(2):
+        s, i, c = ops.route_from_logits(logits, k)
+        off, dest, src = ops.build_permutation(i, c)
+        p = ops.permute_rows(x, src)
+        o = ops.unpermute_combine(p, dest, s, x)
+        n = ops.rmsnorm(x, w, 1e-5, residual=o)
 elif mode == "dense":
     x = torch.randn(4900, 1152, device=dev).bfloat16()
     w = (torch.randn(4304, 1152, device=dev) * 0.02).bfloat16()

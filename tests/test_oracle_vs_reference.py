@@ -33,3 +33,23 @@ def test_moe_layer_live(dtype, T, E, k):
         tied = vals[:, k - 1] == vals[:, k]
         bad = (want.float() - got.float()).abs().amax(-1).view(-1) > 0
         assert not (bad & ~tied).any()
+
+
+def test_installer_rebinds_reference_seams():
+    """aria_b200.install.install() patches the reference MoELayer.forward and the `experts_gemm` global (no GPU needed to
+    check the wiring; executing the patched path needs CUDA)."""
+    from aria_b200 import install, moe_lm as ours
+    ref = load_reference()
+    cfg = ref.moe_lm.AriaMoELMConfig(hidden_size=128, moe_num_experts=8, moe_topk=2, moe_intermediate_size=64,
+                                     moe_num_shared_experts=2, num_hidden_layers=2, num_attention_heads=1, vocab_size=64)
+    model = ref.moe_lm.AriaMoELMForCausalLM(cfg)
+    saved = ref.moe_lm.experts_gemm
+    try:
+        assert install.install(model, ref.moe_lm) == 2
+        assert ref.moe_lm.experts_gemm is ours.experts_gemm
+        layer = model.model.layers[0].mlp
+        assert layer.forward.__func__ is install._moe_forward
+        with pytest.raises(RuntimeError):   # no CPU fallback
+            layer(torch.zeros(1, 4, 128, dtype=torch.bfloat16))
+    finally:
+        ref.moe_lm.experts_gemm = saved
