@@ -83,18 +83,19 @@ __global__ void __launch_bounds__(128) rmsnorm_kernel(const uint4* __restrict__ 
 }
 
 // nn.LayerNorm over the last dim: fp32 mean / variance (two-pass over registers), one rounding at the end.
+// One 128-thread block per row (same reasoning as rmsnorm_kernel).
 template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
+__global__ void __launch_bounds__(128) layernorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
                                                         const uint4* __restrict__ b, uint4* __restrict__ out, int64_t rows,
                                                         int vpr, float eps, float inv_d) {
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
-       r += static_cast<int64_t>(gridDim.x) * wpb) {
+  __shared__ float red[2][4];
+  const int tid = threadIdx.x;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     float h[MAXV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+      const int v = tid + i * 128;
       if (v < vpr) {
         const uint4 q = x[r * vpr + v];
         const uint32_t a[4] = {q.x, q.y, q.z, q.w};
@@ -106,11 +107,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict_
         }
       }
     }
-    const float mean = warp_sum(s) * inv_d;
+    s = warp_sum(s);
+    __syncthreads();
+    if ((tid & 31) == 0) red[0][tid >> 5] = s;
+    __syncthreads();
+    const float mean = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) * inv_d;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+      const int v = tid + i * 128;
       if (v < vpr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -119,10 +124,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict_
         }
       }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(ss) * inv_d + eps);
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[1][tid >> 5] = ss;
+    __syncthreads();
+    const float rstd = 1.0f / sqrtf((red[1][0] + red[1][1] + red[1][2] + red[1][3]) * inv_d + eps);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
+      const int v = tid + i * 128;
       if (v < vpr) {
         const uint4 qw = __ldg(w + v), qb = __ldg(b + v);
         const uint32_t aw[4] = {qw.x, qw.y, qw.z, qw.w}, ab[4] = {qb.x, qb.y, qb.z, qb.w};
@@ -265,16 +273,20 @@ extern "C" int aria_rmsnorm(const void* x, const void* residual, const void* wei
 extern "C" int aria_layernorm(const void* x, const void* weight, const void* bias, void* out, int64_t rows, int32_t d,
                               float eps, aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ARIA_CHECK_ARG(x && weight && bias && out && d % 8 == 0 && d <= 32 * 8 * 10 && rows >= 0);
+  ARIA_CHECK_ARG(x && weight && bias && out && d % 8 == 0 && d <= 128 * 8 * 4 && rows >= 0);
   if (rows == 0) return ARIA_OK;
   const int vpr = d / 8;
-  const int grid = rows_grid(rows, 8);
+  int64_t grid64 = rows;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (grid64 > cap) grid64 = cap;
+  const int grid = static_cast<int>(grid64);
 #define LN(MAXV)                                                                                                    \
-  layernorm_kernel<MAXV><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(weight), \
+  layernorm_kernel<MAXV><<<grid, 128, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(weight), \
                                                    static_cast<const uint4*>(bias), static_cast<uint4*>(out), rows, vpr, eps, 1.0f / d)
-  if (vpr <= 32 * 2) LN(2);
-  else if (vpr <= 32 * 5) LN(5);
-  else LN(10);
+  if (vpr <= 128) LN(1);
+  else if (vpr <= 256) LN(2);
+  else if (vpr <= 384) LN(3);
+  else LN(4);
 #undef LN
   return check_launch("layernorm_kernel");
 }

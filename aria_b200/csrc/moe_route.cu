@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const uint4* __restri
 
 // out[t] = bf16( sum_j bf16(y[dest[t*k+j]] * s[t,j]) ) (+ shared[t] with one more bf16 rounding).
 // One block per token, one 16-byte column per thread: the k gathered rows are k independent loads in flight.
-__global__ void __launch_bounds__(256) combine_kernel(const uint4* __restrict__ y, const int32_t* __restrict__ dest_row,
+__global__ void __launch_bounds__(512) combine_kernel(const uint4* __restrict__ y, const int32_t* __restrict__ dest_row,
                                                       const __nv_bfloat16* __restrict__ scores, const uint4* __restrict__ shared_out,
                                                       uint4* __restrict__ out, int64_t T, int vec_per_row, int k) {
   for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
@@ -286,7 +286,9 @@ extern "C" int aria_unpermute_combine(const void* y, const int32_t* dest_row, co
   if (T == 0) return ARIA_OK;
   int64_t cgrid = T;
   if (cgrid > static_cast<int64_t>(sm_count()) * 16) cgrid = static_cast<int64_t>(sm_count()) * 16;
-  combine_kernel<<<static_cast<int>(cgrid), 256, 0, stream>>>(static_cast<const uint4*>(y), dest_row,
+  int cthreads = (d / 8 + 31) / 32 * 32;  // one 16-byte column per thread, whole row in one pass (d=2560 -> 320 threads)
+  if (cthreads > 512) cthreads = 512;
+  combine_kernel<<<static_cast<int>(cgrid), cthreads, 0, stream>>>(static_cast<const uint4*>(y), dest_row,
                                                            static_cast<const __nv_bfloat16*>(scores),
                                                            static_cast<const uint4*>(shared), static_cast<uint4*>(out), T,
                                                            d / 8, k);
