@@ -317,6 +317,18 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     }
   }
 
+  // HBM-bound grouped regime on the 1-CTA kernel (few rows per expert): 128 x 256 tiles halve the A-tile share of the
+  // L2 -> SM traffic per streamed weight byte (env ARIA_GEMM_WIDE=0 disables, for A/B measurements)
+  if (!two_cta && b_mn && d->num_groups > 1 && BN == 128) {
+    static int wide = -1;
+    if (wide < 0) {
+      const char* ev = getenv("ARIA_GEMM_WIDE");
+      wide = ev ? atoi(ev) : 1;
+    }
+    const bool ok = swiglu ? (d->n % 128 == 0) : (d->n % 256 == 0);
+    if (wide && ok) BN = 256;
+  }
+
   CUtensorMap tmA, tmB[3];
   int rc = make_tmap_2d(&tmA, d->a, d->k, d->m, d->lda * 2, BK, BM);
   if (rc) return rc;
@@ -356,9 +368,11 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     ARIA_LAUNCH(144, false, ARIA_EPI_HEADS);
   }
   if (swiglu) {
+    if (b_mn && BN == 256) ARIA_LAUNCH(256, true, ARIA_EPI_SWIGLU);
     if (b_mn) ARIA_LAUNCH(128, true, ARIA_EPI_SWIGLU);
     ARIA_LAUNCH(128, false, ARIA_EPI_SWIGLU);
   }
+  if (b_mn && BN == 256) ARIA_LAUNCH(256, true, ARIA_EPI_LINEAR);
   if (b_mn) ARIA_LAUNCH(128, true, ARIA_EPI_LINEAR);
   ARIA_LAUNCH(128, false, ARIA_EPI_LINEAR);
 #undef ARIA_LAUNCH
