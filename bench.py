@@ -181,7 +181,7 @@ def run_aria(args, rank, local_rank, world):
     from aria_b200 import _lib as L
     from aria_b200 import ops
     from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration, GraphedPrefill, init_random_
-    from oracle import configs as C  # shapes only (plain dict of model dimensions)
+    from aria_b200 import configs as C
 
     L.load()  # fail loudly if the CUDA extension is missing
     dev = torch.device("cuda", local_rank)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration, init_random_
-from oracle import configs as C
+from aria_b200 import configs as C
 torch.set_grad_enabled(False)
 dev = torch.device("cuda", 0)
 B, Tkv = int(os.environ.get("B", 32)), int(os.environ.get("TKV", 2048))

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 from aria_b200 import ops
 from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration, init_random_
-from oracle import configs as C
+from aria_b200 import configs as C
 torch.set_grad_enabled(False)
 dev = torch.device("cuda", 0)
 T = int(os.environ.get("T", 65536)); layers = int(os.environ.get("LM_LAYERS", 28))

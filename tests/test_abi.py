@@ -102,3 +102,15 @@ def test_offsets_contract():
         moe_lm._as_offsets(torch.zeros(5, dtype=torch.int64), 8, "cpu")  # neither E nor E+1 entries
     with pytest.raises(RuntimeError):
         moe_lm._as_offsets(torch.zeros(9, dtype=torch.int64), 8, "cpu")  # offsets must be int32 CUDA
+
+
+def test_bench_gpu_leg_does_not_touch_oracle():
+    """Only bench.py's cpu_baseline / --impl reference leg may execute oracle/ code."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_aria")
+    body = ast.get_source_segment(src, fn)
+    imports = re.findall(r"^\s*(?:from|import)\s+(\S+)", body, flags=re.M)
+    assert not [m for m in imports if m.startswith("oracle")], imports
+    assert "CpuReference" in body  # the one allowed use: the cpu_baseline leg at N=1
