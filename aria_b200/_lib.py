@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaria_b200.so")
+# ARIA_B200_LIB selects another build of the same C ABI (kernel A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("ARIA_B200_LIB") or os.path.join(_HERE, "libaria_b200.so")
 
 ARIA_OK = 0
 B_NK, B_GKN, B_GNK = 0, 1, 2
@@ -55,6 +56,9 @@ SIGNATURES = {
     "aria_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "aria_combine_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_router_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
+    "aria_router_aux_workspace_bytes": (C.c_size_t, [i32]),
+    "aria_router_aux_loss": (i32, [vp, vp, vp, i64, i32, i32, f32, f32, vp, C.c_size_t, vp]),
+    "aria_router_aux_bwd": (i32, [vp, vp, vp, i64, i32, i32, f32, f32, f32, vp]),
     "aria_permute_rows": (i32, [vp, vp, vp, i64, i32, vp]),
     "aria_unpermute_combine": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_rmsnorm": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, vp]),

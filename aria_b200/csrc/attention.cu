@@ -49,6 +49,12 @@ struct AttnParams {
 //   MMA issue order per key block j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  — tile 1's softmax runs under tile 0's MMAs
 //   and vice versa; tcgen05 ops execute in issue order, which is what makes the S/P aliasing safe.
 constexpr int A2_THREADS = 320;
+#ifndef ARIA_ATTN_P_SPLIT
+#define ARIA_ATTN_P_SPLIT 2
+#endif
+// P is handed to the PV MMA in P_SPLIT key chunks with one mbarrier each, so the first PV k-steps run on the tensor
+// core while the softmax warps are still exponentiating the rest of the row (shortens the S -> P -> PV chain).
+constexpr int P_SPLIT = ARIA_ATTN_P_SPLIT;  // 1, 2 or 4
 constexpr int A2_SMEM = 2 * AT_TILE /*Q*/ + 2 * AT_TILE /*K*/ + 2 * AT_TILE /*V*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
@@ -65,9 +71,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_full = bars + 3;     // [2]
   uint64_t* kv_empty = bars + 5;   // [2]
   uint64_t* s_full = bars + 7;     // [2] per tile
-  uint64_t* p_full = bars + 9;     // [2] per tile
+  uint64_t* p_full = bars + 13;    // [2 tiles][P_SPLIT]
   uint64_t* o_full = bars + 11;    // [2] per tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13 + 2 * P_SPLIT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x % (p.B * p.H);
@@ -94,7 +100,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      for (int c = 0; c < P_SPLIT; ++c) mbar_init(&p_full[i * P_SPLIT + c], 128);
       mbar_init(&o_full[i], 1);
     }
     fence_mbar_init();
@@ -109,7 +115,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       mbar_arrive_expect_tx(q_full, act1 ? 2 * AT_TILE : AT_TILE);
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
       tma_load_4d(sQ + AT_HALF, &tmQ, q_full, 64, q0, h, b);
@@ -129,7 +135,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, false, false);
       const uint32_t idesc_pv = make_idesc_bf16(AT_BM, p.hd_eff, false, true);  // N = hd_eff output columns
       const int qk_steps = p.hd_eff / 16;                                       // columns >= hd_eff are zero padding
@@ -149,9 +155,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t aV = smem_u32(sV + (j & 1) * AT_TILE);
         const uint32_t tP = tmem_base + t * 128;        // bf16 P aliases S_t (2 elements per 32-bit column)
         const uint32_t tO = tmem_base + 256 + t * 128;
+        constexpr int KS = (AT_BN / 16) / P_SPLIT;  // k-steps per P chunk
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)
-          umma_bf16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, AT_HALF, 1024), idesc_pv, (j | k) ? 1u : 0u);
+        for (int c = 0; c < P_SPLIT; ++c) {
+          mbar_wait(&p_full[t * P_SPLIT + c], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) {
+            const int k = c * KS + kk;
+            umma_bf16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, AT_HALF, 1024), idesc_pv, (j | k) ? 1u : 0u);
+          }
+        }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -163,8 +177,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&v_full[s], (j >> 1) & 1);
         bool k_next_ready = false;
         if (j < n_kv0) {
-          mbar_wait(&p_full[0], j & 1);
-          tc_fence_after();
           issue_pv(0, j);
           if (j == n_kv0 - 1) umma_commit(&o_full[0]);
           if (j + 1 < n_kv0) {
@@ -175,8 +187,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         if (j < n_kv1) {
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
           issue_pv(1, j);
           if (j == n_kv1 - 1) umma_commit(&o_full[1]);
           if (j + 1 < n_kv1) {
@@ -267,11 +277,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         // P chunk (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16): S is already in registers
         tmem_st_32x16(tS + c * 16, pk);
+        if ((c + 1) % (4 / P_SPLIT) == 0) {  // chunk of 128/P_SPLIT keys complete -> hand it to the PV MMA
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[t * P_SPLIT + c / (4 / P_SPLIT)]);
+        }
       }
       l += l0 + l1;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
     }
     if (n_kv_t > 0) {
       mbar_wait(&o_full[t], 0);

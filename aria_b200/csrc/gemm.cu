@@ -7,13 +7,25 @@
 
 namespace aria {
 
-template <int BN, bool B_MN, int EPI>
+// pipeline depth: the classic 128-row A stage keeps the tuned depths; skinny-M stages fill ~200 KB (max 24)
+constexpr int gemm_stages(int BN, int AM) {
+  if (AM == 128) return (BN == 256) ? 4 : (BN >= 128 ? 6 : 8);
+  const int s = (200 * 1024) / (AM * BK * 2 + BN * BK * 2);
+  return s > 24 ? 24 : s;
+}
+
+// AM = rows of A staged per k-block (TMA box height).  128 in general; 32 for skinny-M (decode) GEMMs, where a 128-row A
+// stage would be 75 % padding: the shared memory goes to more weight stages instead (bytes in flight are what bound a
+// weight-streaming GEMM).  The MMA still reads 128 rows starting at the stage base; rows >= AM are whatever follows in
+// shared memory and only reach accumulator lanes that the epilogue never stores.
+template <int BN, bool B_MN, int EPI, int AM = 128>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int STAGES = (BN == 256) ? 4 : (BN >= 128 ? 6 : 8);
+  constexpr int A_BYTES = AM * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  constexpr int STAGES = gemm_stages(BN, AM);
   constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   constexpr int OUT_BN = (EPI == ARIA_EPI_SWIGLU) ? BN / 2 : BN;  // output columns per tile
@@ -60,7 +72,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       TileSched sched;
       sched.init(p, n_tiles);
       int stage = 0;
@@ -72,7 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
           if constexpr (B_MN) {
@@ -110,7 +122,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, B_MN);
       const uint32_t a_lbo = 16, a_sbo = 1024;
       const uint32_t b_lbo = p.dbg_lbo ? p.dbg_lbo : (B_MN ? 64 * BK * 2 : 16);
@@ -133,7 +145,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t da = make_smem_desc(sa + k * 32, a_lbo, a_sbo);
@@ -182,13 +194,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   (void)ACC_STRIDE;
 }
 
-template <int BN, bool B_MN, int EPI>
+template <int BN, bool B_MN, int EPI, int AM = 128>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap* tmB, const GemmParams& p, int max_tiles,
                        cudaStream_t stream) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGES = (BN == 256) ? 4 : (BN >= 128 ? 6 : 8);
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
-  auto kern = gemm_kernel<BN, B_MN, EPI>;
+  constexpr int STAGES = gemm_stages(BN, AM);
+  // + (128-AM) rows of slack: the M=128 MMA of the last stage reads 16 KB from a stage base whose A part is only AM rows
+  constexpr int SMEM = STAGES * (AM * BK * 2 + B_STAGE_BYTES) + 1024 /*align*/ + 512 /*barriers*/ + (BM - AM) * BK * 2;
+  auto kern = gemm_kernel<BN, B_MN, EPI, AM>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -329,8 +342,18 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     if (wide && ok) BN = 256;
   }
 
+  // Skinny-M dense GEMMs (decode: m <= 32): 32-row A stages, narrow tiles so that ~80+ CTAs stream weights with many
+  // stages each (bytes in flight bound a weight-streaming GEMM); very wide N (lm_head) keeps 128-column tiles.
+  int AM = 128;
+  static const bool skinny_on = [] { const char* e = getenv("ARIA_GEMM_SKINNY"); return !(e && e[0] == '0'); }();
+  if (skinny_on && !two_cta && !b_mn && d->num_groups == 1 && d->m <= 32 && BN == 128) {
+    AM = 32;
+    if (d->epilogue == ARIA_EPI_LINEAR && d->n_seg == 1 && d->n % 32 == 0 && d->n < 16384) BN = 32;
+    if (swiglu && d->n % 32 == 0) BN = 64;
+  }
+
   CUtensorMap tmA, tmB[3];
-  int rc = make_tmap_2d(&tmA, d->a, d->k, d->m, d->lda * 2, BK, BM);
+  int rc = make_tmap_2d(&tmA, d->a, d->k, d->m, d->lda * 2, BK, AM);
   if (rc) return rc;
   if (b_mn) {
     const uint64_t ncols = swiglu ? 2 * d->n : d->n;
@@ -363,6 +386,15 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     return launch_gemm2_dispatch(BN, b_mn, d->epilogue, tmA, tmB, p, static_cast<int>(max_tiles), stream);
 
 #define ARIA_LAUNCH(BN_, MN_, EPI_) return launch_gemm<BN_, MN_, EPI_>(tmA, tmB, p, static_cast<int>(max_tiles), stream)
+  if (AM == 32) {
+    if (d->epilogue == ARIA_EPI_HEADS) return launch_gemm<128, false, ARIA_EPI_HEADS, 32>(tmA, tmB, p, static_cast<int>(max_tiles), stream);
+    if (swiglu) {
+      if (BN == 64) return launch_gemm<64, false, ARIA_EPI_SWIGLU, 32>(tmA, tmB, p, static_cast<int>(max_tiles), stream);
+      return launch_gemm<128, false, ARIA_EPI_SWIGLU, 32>(tmA, tmB, p, static_cast<int>(max_tiles), stream);
+    }
+    if (BN == 32) return launch_gemm<32, false, ARIA_EPI_LINEAR, 32>(tmA, tmB, p, static_cast<int>(max_tiles), stream);
+    return launch_gemm<128, false, ARIA_EPI_LINEAR, 32>(tmA, tmB, p, static_cast<int>(max_tiles), stream);
+  }
   if (d->epilogue == ARIA_EPI_HEADS) {
     if (BN == 128) ARIA_LAUNCH(128, false, ARIA_EPI_HEADS);
     ARIA_LAUNCH(144, false, ARIA_EPI_HEADS);

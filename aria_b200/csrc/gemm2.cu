@@ -74,7 +74,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       TileSched sched;
       sched.init(p, n_tiles, BM2);
       int stage = 0;
@@ -123,7 +123,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM2, BN, false, B_MN);
       const uint32_t b_lbo = B_MN ? 64 * BK * 2 : 16;
       const uint32_t b_kadv = B_MN ? 16 * 128 : 32;

@@ -76,7 +76,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -105,7 +105,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       constexpr uint32_t idesc = make_idesc_bf16(BM, WG_BN, true, true);  // both operands MN-major
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -251,7 +251,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total; t += n_clusters) {
@@ -282,7 +282,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, WG2_BN, true, true);
       int stage = 0, it = 0;
       uint32_t phase = 0;

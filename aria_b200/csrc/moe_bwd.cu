@@ -123,6 +123,118 @@ __global__ void __launch_bounds__(256) router_bwd_kernel(const float* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Training-mode router losses (moe_lm.py:128-166, 203-241).  The reference never returns their values: they act on the
+// router only through MoEAuxLossAutoScaler.backward (:103-117), which injects d(loss)/d(logits) * main_loss_backward_scale.
+//   z   = c_z * mean_t(lse_t^2)                                  -> dlogits[t,e] += s * c_z * 2 lse_t / T * p[t,e]
+//   aux = c_aux * E/(T k) * sum_e mean_t(p[t,e]) * count_e       -> dlogits[t,e] += s * p[t,e] * (g_e - sum_e' p[t,e'] g_e'),
+//                                                                   g_e = c_aux * E * count_e / (T k T)
+// with p = softmax(logits) in fp32 (:235) and lse = logsumexp(logits).  One warp per token, E <= 256.
+constexpr int AUX_MAX_E = 256;
+
+__device__ __forceinline__ void token_softmax(const __nv_bfloat16* __restrict__ row, int E, int lane, float (&p)[AUX_MAX_E / 32], float& lse) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i) {
+    const int e = lane + i * 32;
+    p[i] = e < E ? __bfloat162float(row[e]) : -INFINITY;
+    mx = fmaxf(mx, p[i]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i) {
+    p[i] = (lane + i * 32 < E) ? __expf(p[i] - mx) : 0.f;
+    sum += p[i];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i) p[i] *= inv;
+  lse = mx + __logf(sum);
+}
+
+// dlogits (bf16, already holding the top-k softmax term from router_bwd_kernel) += loss gradients
+__global__ void __launch_bounds__(256) router_aux_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int32_t* __restrict__ counts,
+                                                             __nv_bfloat16* __restrict__ dlogits, int64_t T, int E, int k, float z_coeff,
+                                                             float aux_coeff, float loss_scale) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float invT = 1.0f / static_cast<float>(T);
+  float g[AUX_MAX_E / 32];
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i) {
+    const int e = lane + i * 32;
+    g[i] = e < E ? aux_coeff * static_cast<float>(E) * static_cast<float>(counts[e]) * invT * invT / static_cast<float>(k) : 0.f;
+  }
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < T; t += static_cast<int64_t>(gridDim.x) * wpb) {
+    float p[AUX_MAX_E / 32], lse;
+    token_softmax(logits + t * E, E, lane, p, lse);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < AUX_MAX_E / 32; ++i) dot += p[i] * g[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float zc = z_coeff * 2.0f * lse * invT;
+#pragma unroll
+    for (int i = 0; i < AUX_MAX_E / 32; ++i) {
+      const int e = lane + i * 32;
+      if (e < E) {
+        const float add = loss_scale * p[i] * (zc + g[i] - dot);
+        dlogits[t * E + e] = __float2bfloat16_rn(__bfloat162float(dlogits[t * E + e]) + add);
+      }
+    }
+  }
+}
+
+// loss values for logging: stage 1 = per-block partial sums [grid][1 + E] (sum lse^2 | sum_t p[t,e]); stage 2 = fixed-order reduce
+__global__ void __launch_bounds__(256) router_aux_partial_kernel(const __nv_bfloat16* __restrict__ logits, float* __restrict__ partial,
+                                                                 int64_t T, int E) {
+  __shared__ float acc[8][AUX_MAX_E + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float ps[AUX_MAX_E / 32], z = 0.f;
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i) ps[i] = 0.f;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * wpb + w; t < T; t += static_cast<int64_t>(gridDim.x) * wpb) {
+    float p[AUX_MAX_E / 32], lse;
+    token_softmax(logits + t * E, E, lane, p, lse);
+    z += lse * lse;
+#pragma unroll
+    for (int i = 0; i < AUX_MAX_E / 32; ++i) ps[i] += p[i];
+  }
+#pragma unroll
+  for (int i = 0; i < AUX_MAX_E / 32; ++i)
+    if (lane + i * 32 < E) acc[w][1 + lane + i * 32] = ps[i];
+  if (lane == 0) acc[w][0] = z;
+  __syncthreads();
+  for (int c = threadIdx.x; c <= E; c += blockDim.x) {
+    float s = 0.f;
+    for (int ww = 0; ww < wpb; ++ww) s += acc[ww][c];
+    partial[static_cast<int64_t>(blockIdx.x) * (E + 1) + c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) router_aux_final_kernel(const float* __restrict__ partial, const int32_t* __restrict__ counts,
+                                                               float* __restrict__ losses, int nblk, int64_t T, int E, int k, float z_coeff,
+                                                               float aux_coeff) {
+  __shared__ float red[AUX_MAX_E + 1];
+  for (int c = threadIdx.x; c <= E; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[static_cast<int64_t>(b) * (E + 1) + c];
+    red[c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float invT = 1.0f / static_cast<float>(T);
+    float aux = 0.f;
+    for (int e = 0; e < E; ++e) aux += red[1 + e] * invT * static_cast<float>(counts[e]);
+    losses[0] = z_coeff * red[0] * invT;
+    losses[1] = aux * (static_cast<float>(E) * invT / static_cast<float>(k)) * aux_coeff;
+  }
+}
+
 static inline int ew_grid(int64_t n, int per_block) {
   int64_t b = (n + per_block - 1) / per_block;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -173,4 +285,32 @@ extern "C" int aria_router_bwd(const float* dscores, const void* scores, const i
   router_bwd_kernel<<<ew_grid(T, 8), 256, 0, stream>>>(dscores, static_cast<const __nv_bfloat16*>(scores), top_idx,
                                                       static_cast<__nv_bfloat16*>(dlogits), T, E, k);
   return check_launch("router_bwd_kernel");
+}
+
+extern "C" size_t aria_router_aux_workspace_bytes(int32_t E) {
+  return static_cast<size_t>(sm_count()) * 4 * static_cast<size_t>(E + 1) * sizeof(float);
+}
+
+extern "C" int aria_router_aux_loss(const void* logits, const int32_t* counts, float* losses, int64_t T, int32_t E, int32_t k,
+                                    float z_coeff, float aux_coeff, void* workspace, size_t ws_bytes, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(logits && counts && losses && workspace && T >= 1 && E >= 1 && E <= AUX_MAX_E && k >= 1);
+  int grid = ew_grid(T, 8);
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+  ARIA_CHECK_ARG(ws_bytes >= static_cast<size_t>(grid) * (E + 1) * sizeof(float));
+  router_aux_partial_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), static_cast<float*>(workspace), T, E);
+  int rc = check_launch("router_aux_partial_kernel");
+  if (rc) return rc;
+  router_aux_final_kernel<<<1, 256, 0, stream>>>(static_cast<const float*>(workspace), counts, losses, grid, T, E, k, z_coeff, aux_coeff);
+  return check_launch("router_aux_final_kernel");
+}
+
+extern "C" int aria_router_aux_bwd(const void* logits, const int32_t* counts, void* dlogits, int64_t T, int32_t E, int32_t k,
+                                   float z_coeff, float aux_coeff, float loss_scale, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(logits && counts && dlogits && T >= 0 && E >= 1 && E <= AUX_MAX_E && k >= 1);
+  if (T == 0) return ARIA_OK;
+  router_aux_bwd_kernel<<<ew_grid(T, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), counts,
+                                                          static_cast<__nv_bfloat16*>(dlogits), T, E, k, z_coeff, aux_coeff, loss_scale);
+  return check_launch("router_aux_bwd_kernel");
 }

@@ -36,7 +36,7 @@ class AriaMoELMConfig:
 
     def __init__(self, hidden_size=4096, num_attention_heads=32, num_hidden_layers=32, vocab_size=32000,
                  moe_intermediate_size=4096, moe_num_experts=8, moe_topk=2, moe_num_shared_experts=2,
-                 rms_norm_eps=1e-6, rope_theta=10000.0, **_ignored):
+                 moe_z_loss_coeff=1e-5, moe_aux_loss_coeff=1e-3, rms_norm_eps=1e-6, rope_theta=10000.0, **_ignored):
         self.hidden_size = hidden_size
         self.num_attention_heads = num_attention_heads
         self.num_hidden_layers = num_hidden_layers
@@ -45,9 +45,22 @@ class AriaMoELMConfig:
         self.moe_num_experts = moe_num_experts
         self.moe_topk = moe_topk
         self.moe_num_shared_experts = moe_num_shared_experts
+        self.moe_z_loss_coeff = moe_z_loss_coeff      # training-mode router losses (moe_lm.py:57-58); used by moe_train
+        self.moe_aux_loss_coeff = moe_aux_loss_coeff
         self.rms_norm_eps = rms_norm_eps
         self.rope_theta = rope_theta
         self.head_dim = hidden_size // num_attention_heads
+
+
+class MoEAuxLossAutoScaler:
+    """Holder of the scale applied to the router-loss gradients (reference `MoEAuxLossAutoScaler`, moe_lm.py:84-125: the
+    aux losses never enter the returned loss, their gradient is injected with this scale in backward)."""
+
+    main_loss_backward_scale: float = 1.0
+
+    @staticmethod
+    def set_loss_scale(scale):
+        MoEAuxLossAutoScaler.main_loss_backward_scale = float(scale)
 
 
 def _param(*shape, device=None):

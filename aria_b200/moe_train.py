@@ -8,7 +8,9 @@ gradient is an explicit kernel:
                -> glu backward -> fc1 wgrad + dgrad -> un-permute sum -> shared-expert dgrad/wgrad -> top-k softmax backward
                -> router wgrad + dgrad
 
-Eval-mode routing (the training-only z-loss / aux-loss side effects, moe_lm.py:84-166, are not part of this round).
+Router losses: with `router_losses=True` (the reference's `self.training` branch, moe_lm.py:257-258,271-272) the z-loss and
+load-balancing-loss gradients (moe_lm.py:84-166) are added to dlogits by `aria_router_aux_bwd`, scaled by
+`MoEAuxLossAutoScaler.main_loss_backward_scale`; the default (False) is eval-mode routing, which is what BASELINE cfg 5 times.
 Gradients are bf16 tensors accumulated in fp32 inside the tensor-core kernels.
 """
 from __future__ import annotations
@@ -21,7 +23,7 @@ from . import ops
 
 class MoELayerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_router, fc1, fc2, gate_w, up_w, down_w, topk: int):
+    def forward(ctx, x, w_router, fc1, fc2, gate_w, up_w, down_w, topk: int, loss_coeffs=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1]).contiguous()
         E = w_router.shape[0]
@@ -39,6 +41,9 @@ class MoELayerFunction(torch.autograd.Function):
         out = ops.unpermute_combine(y, dest, scores, shared)
         ctx.save_for_backward(x2, w_router, fc1, fc2, gate_w, up_w, down_w, scores, idx, offsets, dest, xp, h1, h, y, hs1, hs)
         ctx.topk = topk
+        ctx.loss_coeffs = loss_coeffs
+        if loss_coeffs is not None:  # keep what the loss gradients need: the bf16 logits and tokens_per_expert
+            ctx.router_logits, ctx.counts = _logits, counts
         ctx.shape = shape
         return out.view(shape)
 
@@ -67,16 +72,24 @@ class MoELayerFunction(torch.autograd.Function):
         dx = ops.matmul_kn(dhs1[:, Is:], up_w, residual=dx)
         # ---- router
         dlogits = ops.router_bwd(dscores, scores, idx, E)                     # [T, E]
+        if ctx.loss_coeffs is not None:
+            from .moe_lm import MoEAuxLossAutoScaler
+            z_c, aux_c = ctx.loss_coeffs
+            ops.router_aux_bwd(ctx.router_logits, ctx.counts, dlogits, ctx.topk, z_c, aux_c,
+                               MoEAuxLossAutoScaler.main_loss_backward_scale)
         d_router = ops.grouped_wgrad(dlogits, x2, dense)[0]                   # [E, d]
         dx = ops.matmul_kn(dlogits, w_router, residual=dx)
         # ---- un-permute: dx[t] += sum_j dxp[dest[t, j]]
         ones = torch.ones_like(scores)
         dx = ops.unpermute_combine(dxp, dest, ones, dx)
-        return dx.view(ctx.shape), d_router, d_fc1, d_fc2, d_gate, d_up, d_down, None
+        return dx.view(ctx.shape), d_router, d_fc1, d_fc2, d_gate, d_up, d_down, None, None
 
 
-def moe_layer_train(layer, hidden_states: torch.Tensor) -> torch.Tensor:
-    """Differentiable `MoELayer.forward` for an `aria_b200.moe_lm.MoELayer` whose parameters require grad."""
+def moe_layer_train(layer, hidden_states: torch.Tensor, router_losses: bool = False) -> torch.Tensor:
+    """Differentiable `MoELayer.forward` for an `aria_b200.moe_lm.MoELayer` whose parameters require grad.
+    router_losses=True adds the training-mode z-loss / load-balancing-loss gradients (coefficients from the config)."""
+    cfg = layer.router.config
+    coeffs = (float(cfg.moe_z_loss_coeff), float(cfg.moe_aux_loss_coeff)) if router_losses else None
     return MoELayerFunction.apply(hidden_states, layer.router.weight, layer.experts.fc1.weight, layer.experts.fc2.weight,
                                   layer.shared_experts.gate_proj.weight, layer.shared_experts.up_proj.weight,
-                                  layer.shared_experts.down_proj.weight, layer.router.config.moe_topk)
+                                  layer.shared_experts.down_proj.weight, cfg.moe_topk, coeffs)

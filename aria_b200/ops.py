@@ -232,6 +232,31 @@ def router_bwd(dscores: torch.Tensor, scores: torch.Tensor, top_idx: torch.Tenso
     return dl
 
 
+def router_aux_loss(logits: torch.Tensor, counts: torch.Tensor, k: int, z_coeff: float, aux_coeff: float) -> torch.Tensor:
+    """[z_loss, aux_loss] (fp32) of the training-mode router (moe_lm.py:128-166); values are for logging only."""
+    _chk(logits), _chk(counts, torch.int32)
+    T, E = logits.shape
+    lib = L.load()
+    nbytes = lib.aria_router_aux_workspace_bytes(E)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        L.check(lib.aria_router_aux_loss(_p(logits), _p(counts), _p(out), T, E, k, z_coeff, aux_coeff, _p(ws), nbytes,
+                                         _stream(logits)), "router_aux_loss")
+    return out
+
+
+def router_aux_bwd(logits: torch.Tensor, counts: torch.Tensor, dlogits: torch.Tensor, k: int, z_coeff: float, aux_coeff: float,
+                   loss_scale: float = 1.0) -> torch.Tensor:
+    """dlogits += loss_scale * d(z_loss + aux_loss)/d(logits)  (MoEAuxLossAutoScaler.backward, moe_lm.py:103-117), in place."""
+    _chk(logits), _chk(counts, torch.int32), _chk(dlogits)
+    T, E = logits.shape
+    with torch.cuda.device(logits.device):
+        L.check(L.load().aria_router_aux_bwd(_p(logits), _p(counts), _p(dlogits), T, E, k, z_coeff, aux_coeff, loss_scale,
+                                             _stream(logits)), "router_aux_bwd")
+    return dlogits
+
+
 def qkv_heads(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
               outs: Sequence[torch.Tensor], head_dim: int, rows_per_batch: int, pos0: int = 0, rope_mask: int = 0,
               rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,

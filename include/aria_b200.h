@@ -144,6 +144,18 @@ int aria_combine_bwd(const void* dout, const void* y, const int32_t* dest_row, c
 /* backward of softmax-over-top-k (moe_lm.py:261-262): dlogits[t, idx[t,j]] = s_j * (g_j - sum_i s_i g_i), zeros elsewhere. */
 int aria_router_bwd(const float* dscores, const void* scores, const int32_t* top_idx, void* dlogits, int64_t T, int32_t E,
                     int32_t k, aria_stream_t stream);
+/* Training-mode router losses (TopKRouter.apply_z_loss / apply_aux_loss, moe_lm.py:203-241; z_loss_func :128-140,
+ * switch_load_balancing_loss_func :143-166).  logits [T,E] bf16, counts [E] int32 (tokens_per_expert), E <= 256.
+ *   losses[0] = z_coeff * mean_t(logsumexp(logits_t)^2)
+ *   losses[1] = aux_coeff * E/(T*k) * sum_e mean_t(softmax(logits)_te) * counts[e]          (fp32 softmax, :235)
+ * The reference uses the values only through MoEAuxLossAutoScaler (:84-125): aria_router_aux_bwd ADDS
+ * loss_scale * d(losses[0] + losses[1])/d(logits) to dlogits (bf16 [T,E], e.g. the output of aria_router_bwd);
+ * loss_scale is MoEAuxLossAutoScaler.main_loss_backward_scale. */
+size_t aria_router_aux_workspace_bytes(int32_t E);
+int aria_router_aux_loss(const void* logits, const int32_t* counts, float* losses, int64_t T, int32_t E, int32_t k, float z_coeff,
+                         float aux_coeff, void* workspace, size_t ws_bytes, aria_stream_t stream);
+int aria_router_aux_bwd(const void* logits, const int32_t* counts, void* dlogits, int64_t T, int32_t E, int32_t k, float z_coeff,
+                        float aux_coeff, float loss_scale, aria_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Norms, RoPE table, embedding, patches

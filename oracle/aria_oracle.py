@@ -49,16 +49,62 @@ def router_gating(x: Tensor, w_router: Tensor) -> Tensor:
 
 def topk_lowest_index(logits: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """moe_lm.py:261 `torch.topk(logits, k, dim=1)` with the tie rule made explicit (see header)."""
-    vals, idx = torch.sort(logits.float(), dim=1, descending=True, stable=True)
-    return vals[:, :k].to(logits.dtype), idx[:, :k]
+    idx = torch.sort(logits.detach().float(), dim=1, descending=True, stable=True).indices[:, :k]
+    return torch.gather(logits, 1, idx), idx
 
 
-def router_routing(logits: Tensor, k: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """moe_lm.py:243-273 eval path: topk -> softmax(fp32)->dtype -> per-expert histogram."""
+class _LossGradInjector(torch.autograd.Function):
+    """moe_lm.py:84-125 `MoEAuxLossAutoScaler`: identity on `passthrough`; in backward the attached loss receives the
+    gradient `scale` (so the loss acts only through d(loss)/d(logits) * scale, never through its value)."""
+
+    scale = 1.0
+
+    @staticmethod
+    def forward(ctx, passthrough, loss):
+        ctx.save_for_backward(loss)
+        return passthrough
+
+    @staticmethod
+    def backward(ctx, grad):
+        (loss,) = ctx.saved_tensors
+        return grad, torch.ones_like(loss) * _LossGradInjector.scale
+
+
+def z_loss(logits: Tensor, coeff: float) -> Tensor:
+    """moe_lm.py:128-140: mean over tokens of logsumexp(logits)^2, times the coefficient (in the logits dtype)."""
+    return torch.logsumexp(logits, dim=-1).square().mean() * coeff
+
+
+def load_balancing_loss(probs: Tensor, counts: Tensor, k: int, coeff: float) -> Tensor:
+    """moe_lm.py:143-166 (Switch): sum_e mean_t(probs)_e * count_e * E / (T*k) * coeff."""
+    T, E = probs.shape
+    return (probs.mean(dim=0) * counts).sum() * (E / (T * k) * coeff)
+
+
+def router_routing(logits: Tensor, k: int, loss_coeffs: Optional[Tuple[float, float]] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """moe_lm.py:243-273: topk -> softmax(fp32)->dtype -> per-expert histogram.  `loss_coeffs=(z, aux)` selects the
+    `self.training` branch (:257-258, :271-272): z-loss attached to the logits before top-k, load-balancing loss
+    (fp32 softmax over all experts, :235) attached to the scores."""
+    if loss_coeffs is not None:
+        logits = _LossGradInjector.apply(logits, z_loss(logits, loss_coeffs[0]))
     top_logits, top_idx = topk_lowest_index(logits, k)
     scores = torch.softmax(top_logits, dim=-1, dtype=torch.float32).type_as(logits)
     counts = torch.bincount(top_idx.flatten(), minlength=logits.shape[1])  # == histc, :264-269
+    if loss_coeffs is not None:
+        probs = torch.softmax(logits, dim=-1, dtype=torch.float32)
+        scores = _LossGradInjector.apply(scores, load_balancing_loss(probs, counts, k, loss_coeffs[1]))
     return scores, top_idx, counts
+
+
+def router_loss_grad(logits: Tensor, counts: Tensor, k: int, z_coeff: float, aux_coeff: float, scale: float = 1.0) -> Tensor:
+    """Closed form (fp32) of what the two attached losses add to d/d(logits):
+    scale * p * (2 c_z lse / T + g - <p, g>),  g_e = c_aux * E * count_e / (T k T),  p = softmax(logits), lse = logsumexp."""
+    lf = logits.float()
+    T, E = lf.shape
+    p = torch.softmax(lf, dim=-1)
+    lse = torch.logsumexp(lf, dim=-1, keepdim=True)
+    g = (aux_coeff * E / (T * k * T)) * counts.float()[None, :]
+    return scale * p * (2.0 * z_coeff * lse / T + g - (p * g).sum(-1, keepdim=True))
 
 
 def token_permutation(x: Tensor, top_idx: Tensor, k: int) -> Tuple[Tensor, Tensor]:
@@ -107,14 +153,15 @@ def shared_expert_mlp(x: Tensor, gate_w: Tensor, up_w: Tensor, down_w: Tensor) -
     return F.linear(F.silu(F.linear(x, gate_w)) * F.linear(x, up_w), down_w)
 
 
-def moe_layer(x: Tensor, w: Dict[str, Tensor], k: int, prefix: str = "", return_parts: bool = False):
+def moe_layer(x: Tensor, w: Dict[str, Tensor], k: int, prefix: str = "", return_parts: bool = False,
+              loss_coeffs: Optional[Tuple[float, float]] = None):
     """moe_lm.py:548-577 `MoELayer.forward`.  `w` uses the reference parameter names:
     router.weight [E,d], experts.fc1.weight [E,d,2I], experts.fc2.weight [E,I,d],
     shared_experts.{gate,up,down}_proj.weight."""
     shape = x.shape
     x2 = x.reshape(-1, shape[-1])
     logits = router_gating(x2, w[prefix + "router.weight"])
-    scores, top_idx, counts = router_routing(logits, k)
+    scores, top_idx, counts = router_routing(logits, k, loss_coeffs)
     permuted, order = token_permutation(x2, top_idx, k)
     y = grouped_mlp(permuted, w[prefix + "experts.fc1.weight"], w[prefix + "experts.fc2.weight"], counts)
     out = token_unpermutation(y, order, scores, k).view(shape)

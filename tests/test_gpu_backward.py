@@ -108,3 +108,73 @@ def test_wgrad_two_cta_path_and_sources():
             assert float(got[e].abs().max()) == 0.0
         else:
             assert _rel_l2(got[e], want) <= 1e-2
+
+
+@pytest.mark.parametrize("T,E,k", [(40, 8, 2), (777, 64, 6), (33, 200, 4)])
+def test_router_aux_loss_kernels_vs_oracle(T, E, k):
+    """Training-mode router losses (moe_lm.py:128-166, 203-241): loss values and the gradient they inject, against the
+    oracle's fp32 closed form (pinned to the reference's autograd in tests/test_oracle_vs_reference.py)."""
+    from aria_b200 import ops
+    from oracle import aria_oracle as O
+    g = torch.Generator().manual_seed(T + E)
+    logits = (torch.randn(T, E, generator=g) * 3).bfloat16()
+    _, _, counts = O.router_routing(logits, k)
+    z_c, aux_c, scale = 0.3, 1.7, 8.0
+    base = (torch.randn(T, E, generator=g) * 1e-3).bfloat16()      # what router_bwd left in dlogits
+    want = base.float() + O.router_loss_grad(logits, counts, k, z_c, aux_c, scale)
+    dl = base.clone().to(DEV)
+    ops.router_aux_bwd(logits.to(DEV), counts.to(torch.int32).to(DEV), dl, k, z_c, aux_c, scale)
+    err = (dl.float().cpu() - want).abs().max() / want.abs().max()
+    assert float(err) <= 1e-2, float(err)      # one bf16 rounding of the sum
+    losses = ops.router_aux_loss(logits.to(DEV), counts.to(torch.int32).to(DEV), k, z_c, aux_c).cpu()
+    z = O.z_loss(logits.float(), z_c)
+    aux = O.load_balancing_loss(torch.softmax(logits.float(), -1), counts, k, aux_c)
+    assert abs(float(losses[0]) - float(z)) <= 1e-4 * abs(float(z))
+    assert abs(float(losses[1]) - float(aux)) <= 1e-4 * abs(float(aux))
+
+
+def test_moe_layer_train_with_router_losses_vs_oracle_autograd():
+    """moe_layer_train(router_losses=True): the router gradient picks up the z-loss / load-balancing terms scaled by
+    MoEAuxLossAutoScaler.main_loss_backward_scale (oracle: the same losses attached through autograd)."""
+    from aria_b200 import moe_lm, moe_train
+    from oracle import aria_oracle as O
+    from oracle import configs as C
+    T, E, k, d, I = 96, 16, 4, 256, 128
+    tc = dict(hidden_size=d, moe_num_experts=E, moe_topk=k, moe_intermediate_size=I, moe_num_shared_experts=2,
+              moe_z_loss_coeff=0.5, moe_aux_loss_coeff=2.0)
+    gen = torch.Generator().manual_seed(11)
+    sd = {n: v.bfloat16() for n, v in C.moe_layer_state(tc, gen).items()}
+    sd["router.weight"] = (sd["router.weight"].float() * 20).bfloat16()
+    x = torch.randn(1, T, d, generator=gen).bfloat16()
+    gout = (torch.randn(1, T, d, generator=gen) * 0.01).bfloat16()     # small main gradient: the loss terms dominate d_router
+    scale = 4.0
+    sd32 = {n: v.float().requires_grad_(True) for n, v in sd.items()}
+    x32 = x.float().requires_grad_(True)
+    O._LossGradInjector.scale = scale
+    try:
+        with torch.enable_grad():
+            want, parts = O.moe_layer(x32, sd32, k, return_parts=True, loss_coeffs=(0.5, 2.0))
+            want.backward(gout.float())
+    finally:
+        O._LossGradInjector.scale = 1.0
+    layer = moe_lm.MoELayer(moe_lm.AriaMoELMConfig(**tc), device=DEV)
+    layer.load_state_dict({n: v.to(DEV) for n, v in sd.items()}, strict=True)
+    for p_ in layer.parameters():
+        p_.requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    moe_lm.MoEAuxLossAutoScaler.set_loss_scale(scale)
+    try:
+        with torch.enable_grad():
+            moe_train.moe_layer_train(layer, xg, router_losses=True).backward(gout.to(DEV))
+        d_router_train = layer.router.weight.grad.clone()
+        layer.router.weight.grad = None
+        xg2 = x.to(DEV).requires_grad_(True)
+        with torch.enable_grad():
+            moe_train.moe_layer_train(layer, xg2).backward(gout.to(DEV))
+        d_router_eval = layer.router.weight.grad.clone()
+    finally:
+        moe_lm.MoEAuxLossAutoScaler.set_loss_scale(1.0)
+    # the loss terms must be visible (otherwise this test checks nothing) ...
+    assert _rel_l2(d_router_train, d_router_eval) > 0.5
+    # ... and match the oracle: they depend on the logits only smoothly, so near-tie flips do not matter much here
+    assert _rel_l2(d_router_train, sd32["router.weight"].grad) <= 3e-2

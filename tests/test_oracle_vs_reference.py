@@ -53,3 +53,60 @@ def test_installer_rebinds_reference_seams():
             layer(torch.zeros(1, 4, 128, dtype=torch.bfloat16))
     finally:
         ref.moe_lm.experts_gemm = saved
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("scale", [1.0, 64.0])
+def test_moe_layer_training_losses_backward_live(dtype, scale):
+    """Training-mode routing (z-loss + load-balancing loss injected through MoEAuxLossAutoScaler, moe_lm.py:84-166,
+    203-241): gradients of the unmodified reference vs the oracle's restatement, and vs the closed form the CUDA kernel
+    implements (O.router_loss_grad)."""
+    ref = load_reference()
+    T, E, k, d = 48, 16, 4, 128
+    # large coefficients so the loss terms are well above bf16 noise of the main gradient
+    tc = dict(hidden_size=d, moe_num_experts=E, moe_topk=k, moe_intermediate_size=64, moe_num_shared_experts=2,
+              moe_z_loss_coeff=0.5, moe_aux_loss_coeff=2.0)
+    gen = torch.Generator().manual_seed(5)
+    sd = {n: v.to(dtype) for n, v in C.moe_layer_state(tc, gen).items()}
+    sd["router.weight"] = (sd["router.weight"].float() * 20).to(dtype)   # spread the logits
+    x0 = torch.randn(1, T, d, generator=gen).to(dtype)
+    dout = torch.randn(1, T, d, generator=gen).to(dtype)
+    with torch.enable_grad():
+        layer = ref.moe_lm.MoELayer(ref.moe_lm.AriaMoELMConfig(**tc))
+        layer.load_state_dict(sd, strict=True)
+        layer = layer.to(dtype).train()
+        ref.moe_lm.MoEAuxLossAutoScaler.set_loss_scale(torch.tensor(scale))
+        try:
+            xr = x0.clone().requires_grad_(True)
+            layer(xr).backward(dout)
+        finally:
+            ref.moe_lm.MoEAuxLossAutoScaler.set_loss_scale(torch.tensor(1.0))
+        want = {n: p.grad for n, p in layer.named_parameters()}
+        w = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+        xo = x0.clone().requires_grad_(True)
+        O._LossGradInjector.scale = scale
+        try:
+            O.moe_layer(xo, w, k, loss_coeffs=(0.5, 2.0)).backward(dout)
+        finally:
+            O._LossGradInjector.scale = 1.0
+        # eval-mode oracle (no losses): the difference of the router gradients is the loss contribution
+        w0 = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+        x1 = x0.clone().requires_grad_(True)
+        O.moe_layer(x1, w0, k).backward(dout)
+    tol = 1e-6 if dtype == torch.float32 else 0.0
+    for n in want:
+        assert (want[n].float() - w[n].grad.float()).abs().max() <= tol * max(1.0, float(want[n].float().abs().max())), n
+    # dx sums three branches (router, dispatch, shared expert); autograd's bf16 accumulation order is an engine detail,
+    # so in bf16 it is only checked to an ulp-level tolerance (the parameter gradients above are bit-exact)
+    xtol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert (xr.grad.float() - xo.grad.float()).abs().max() <= xtol * max(1.0, float(xr.grad.float().abs().max()))
+    # closed form: d_router(train) - d_router(eval) == router_loss_grad^T @ x
+    x2 = x0.reshape(T, d)
+    logits = O.router_gating(x2, sd["router.weight"])
+    _, _, counts = O.router_routing(logits, k)
+    dl = O.router_loss_grad(logits, counts, k, 0.5, 2.0, scale)
+    assert float(dl.abs().max()) > 0
+    delta = w["router.weight"].grad.float() - w0["router.weight"].grad.float()
+    closed = dl.t() @ x2.float()
+    rel = (delta - closed).abs().max() / closed.abs().max()
+    assert rel <= (1e-4 if dtype == torch.float32 else 4e-2), float(rel)
