@@ -139,31 +139,37 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, false, false);
       const uint32_t idesc_pv = make_idesc_bf16(AT_BM, p.hd_eff, false, true);  // N = hd_eff output columns
       const int qk_steps = p.hd_eff / 16;                                       // columns >= hd_eff are zero padding
+      // This thread's instruction stream is the critical path of the whole kernel (32 MMAs per key block for the two
+      // tiles): descriptors are base + offset adds, barrier addresses plain 32-bit values.
+      const uint64_t dQ0 = make_smem_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t dK0 = make_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t dV0 = make_smem_desc(smem_u32(sV), AT_HALF, 1024);
+      const uint32_t s_full0 = smem_u32(s_full), p_full0 = smem_u32(p_full);
       auto issue_qk = [&](int t, int j) {
-        const uint32_t aQ = smem_u32(sQ + t * AT_TILE);
-        const uint32_t aK = smem_u32(sK + (j & 1) * AT_TILE);
+        const uint64_t dQ = dQ0 + t * (AT_TILE >> 4);
+        const uint64_t dK = dK0 + (j & 1) * (AT_TILE >> 4);
         const uint32_t tS = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k) {
           if (k >= qk_steps) break;
-          const uint32_t off = (k >> 2) * AT_HALF + (k & 3) * 32;
-          umma_bf16_ss(tS, make_smem_desc(aQ + off, 16, 1024), make_smem_desc(aK + off, 16, 1024), idesc_qk, k ? 1u : 0u);
+          const uint32_t off = ((k >> 2) * AT_HALF + (k & 3) * 32) >> 4;
+          umma_bf16_ss(tS, dQ + off, dK + off, idesc_qk, k ? 1u : 0u);
         }
-        umma_commit(&s_full[t]);
+        umma_commit_addr(s_full0 + t * 8);
       };
       auto issue_pv = [&](int t, int j) {
-        const uint32_t aV = smem_u32(sV + (j & 1) * AT_TILE);
+        const uint64_t dV = dV0 + (j & 1) * (AT_TILE >> 4);
         const uint32_t tP = tmem_base + t * 128;        // bf16 P aliases S_t (2 elements per 32-bit column)
         const uint32_t tO = tmem_base + 256 + t * 128;
         constexpr int KS = (AT_BN / 16) / P_SPLIT;  // k-steps per P chunk
 #pragma unroll
         for (int c = 0; c < P_SPLIT; ++c) {
-          mbar_wait(&p_full[t * P_SPLIT + c], j & 1);
+          mbar_wait_addr(p_full0 + (t * P_SPLIT + c) * 8, j & 1);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < KS; ++kk) {
             const int k = c * KS + kk;
-            umma_bf16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, AT_HALF, 1024), idesc_pv, (j | k) ? 1u : 0u);
+            umma_bf16_ts(tO, tP + k * 8, dV + k * (2048 >> 4), idesc_pv, (j | k) ? 1u : 0u);
           }
         }
       };

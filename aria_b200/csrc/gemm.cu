@@ -70,26 +70,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int n_tiles = (n_out_total + OUT_BN - 1) / OUT_BN;
   const int k_blocks = (p.K + BK - 1) / BK;
 
+  // The two single-thread loops below are latency-bound instruction streams: every SASS instruction in them costs ~5-10
+  // cycles of k-block time (measured with scripts/probes/mma_probe.cu: 0.32 us per k-block in the naive form, 0.12-0.15 us
+  // when lean).  Hence: elect.sync guards (no vector->uniform register waterfalls), everything tile-invariant hoisted out of
+  // the k loop, shared-memory addresses as running 32-bit values, descriptors as base + offset.
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
+    if (elect_one()) {
       TileSched sched;
       sched.init(p, n_tiles);
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x;; t += gridDim.x) {
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int a_row = row0 + m_idx * BM;
+        const int bgrp = p.group_mod ? grp % p.group_mod : grp;
+        // B coordinates of this tile (k-invariant part)
+        int b_c0 = 0, b_c1 = 0;          // K-major: row (n) coordinate of the two boxes; MN-major: base k row
+        const CUtensorMap* tb0 = &tmB0;
+        const CUtensorMap* tb1 = &tmB1;
+        if constexpr (B_MN) {
+          b_c0 = bgrp * p.K;
+        } else if constexpr (EPI == ARIA_EPI_SWIGLU) {
+          b_c0 = b_c1 = n_idx * OUT_BN;
+        } else {
+          const int col = n_idx * BN;
+          const int seg = col / p.N;
+          tb0 = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
+          b_c0 = col - seg * p.N + bgrp * p.b_group_rows;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+          const uint32_t fb = full0 + stage * 8;
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          mbar_wait_addr(empty0 + stage * 8, phase ^ 1);
+          mbar_arrive_expect_tx_addr(fb, STAGE_BYTES);
+          tma_load_2d_addr(sa, &tmA, fb, kb * BK, a_row);
           if constexpr (B_MN) {
             // B = [G*K, Ncols] rows k, N contiguous; one box = 64 k-rows x 64 n (8 KB), BN/64 boxes per stage
-            const int krow = (p.group_mod ? grp % p.group_mod : grp) * p.K + kb * BK;
+            const int krow = b_c0 + kb * BK;
             constexpr int CH = BN / 64;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
@@ -100,18 +121,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               } else {
                 ncol = n_idx * BN + c * 64;
               }
-              tma_load_2d(sb + c * (64 * BK * 2), &tmB0, &full_bar[stage], ncol, krow);
+              tma_load_2d_addr(sb + c * (64 * BK * 2), &tmB0, fb, ncol, krow);
             }
+          } else if constexpr (EPI == ARIA_EPI_SWIGLU) {
+            tma_load_2d_addr(sb, tb0, fb, kb * BK, b_c0);
+            tma_load_2d_addr(sb + (BN / 2) * BK * 2, tb1, fb, kb * BK, b_c1);
           } else {
-            if constexpr (EPI == ARIA_EPI_SWIGLU) {
-              tma_load_2d(sb, &tmB0, &full_bar[stage], kb * BK, n_idx * OUT_BN);
-              tma_load_2d(sb + (BN / 2) * BK * 2, &tmB1, &full_bar[stage], kb * BK, n_idx * OUT_BN);
-            } else {
-              const int col = n_idx * BN;
-              const int seg = col / p.N;
-              const CUtensorMap* tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-              tma_load_2d(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + (p.group_mod ? grp % p.group_mod : grp) * p.b_group_rows);
-            }
+            tma_load_2d_addr(sb, tb0, fb, kb * BK, b_c0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -122,43 +138,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, B_MN);
-      const uint32_t a_lbo = 16, a_sbo = 1024;
       const uint32_t b_lbo = p.dbg_lbo ? p.dbg_lbo : (B_MN ? 64 * BK * 2 : 16);
       const uint32_t b_sbo = p.dbg_sbo ? p.dbg_sbo : 1024;
-      const uint32_t b_kadv = p.dbg_kadv ? p.dbg_kadv : (B_MN ? 16 * 128 : 32);
+      const uint32_t b_kadv = (p.dbg_kadv ? p.dbg_kadv : (B_MN ? 16 * 128 : 32)) >> 4;
+      // descriptors of stage 0 / k-step 0; the start-address field is (addr >> 4) in the low 14 bits and shared-memory
+      // addresses stay below 2^18, so adding (byte offset >> 4) never carries into the next field
+      const uint64_t da0 = make_smem_desc(smem_base, 16, 1024);
+      const uint64_t db0 = make_smem_desc(smem_base + A_BYTES, b_lbo, b_sbo);
+      const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
       TileSched sched;
       sched.init(p, n_tiles);
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int t = blockIdx.x;; t += gridDim.x, ++it) {
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_addr(tempty0 + as * 8, aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_addr(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = da0 + stage * (STAGE_BYTES >> 4);
+          const uint64_t db = db0 + stage * (STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t da = make_smem_desc(sa + k * 32, a_lbo, a_sbo);
-            uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, b_sbo);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + k * 2, db + k * b_kadv, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_addr(empty0 + stage * 8);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        umma_commit_addr(tfull0 + as * 8);  // accumulator complete -> epilogue
       }
     }
   } else {

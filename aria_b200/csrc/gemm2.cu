@@ -72,26 +72,44 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int n_tiles = (n_out_total + OUT_BN - 1) / OUT_BN;
   const int k_blocks = (p.K + BK - 1) / BK;
 
+  // Lean single-thread issue loops (see gemm.cu): tile-invariant math hoisted, 32-bit shared addresses, base descriptors.
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
-    if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
+    if (elect_one()) {
       TileSched sched;
       sched.init(p, n_tiles, BM2);
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
+      const uint32_t leader_full0 = full0 & 0xFEFFFFFFu;  // completion bytes are credited to the leader CTA's barrier
       for (int t = cluster_id;; t += n_clusters) {
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int a_row = row0 + m_idx * BM2 + static_cast<int>(rank) * BM;
+        const int bgrp = p.group_mod ? grp % p.group_mod : grp;
+        int b_c = 0;
+        const CUtensorMap* tb = &tmB0;
+        if constexpr (B_MN) {
+          b_c = bgrp * p.K;
+        } else if constexpr (EPI == ARIA_EPI_SWIGLU) {
+          tb = rank == 0 ? &tmB0 : &tmB1;
+          b_c = n_idx * OUT_BN;
+        } else {
+          const int col = n_idx * BN;
+          const int seg = col / p.N;
+          tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
+          b_c = col - seg * p.N + static_cast<int>(rank) * BH + bgrp * p.b_group_rows;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, a_row);
+          const uint32_t fb = leader_full0 + stage * 8;
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          mbar_wait_addr(empty0 + stage * 8, phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx_addr(full0 + stage * 8, 2 * STAGE_BYTES);
+          tma_load_2d_2sm_addr(sa, &tmA, fb, kb * BK, a_row);
           if constexpr (B_MN) {
             // B = [G*K, Ncols], N contiguous.  This CTA stages N-columns [rank*BH, +BH) of the tile.
-            const int krow = (p.group_mod ? grp % p.group_mod : grp) * p.K + kb * BK;
+            const int krow = b_c + kb * BK;
             constexpr int CH = BH / 64;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
@@ -102,17 +120,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               } else {
                 ncol = n_idx * BN + static_cast<int>(rank) * BH + c * 64;
               }
-              tma_load_2d_2sm(sb + c * (64 * BK * 2), &tmB0, &full_bar[stage], ncol, krow);
+              tma_load_2d_2sm_addr(sb + c * (64 * BK * 2), &tmB0, fb, ncol, krow);
             }
           } else {
-            if constexpr (EPI == ARIA_EPI_SWIGLU) {
-              tma_load_2d_2sm(sb, rank == 0 ? &tmB0 : &tmB1, &full_bar[stage], kb * BK, n_idx * OUT_BN);
-            } else {
-              const int col = n_idx * BN;
-              const int seg = col / p.N;
-              const CUtensorMap* tb = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-              tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * BK, col - seg * p.N + static_cast<int>(rank) * BH + (p.group_mod ? grp % p.group_mod : grp) * p.b_group_rows);
-            }
+            tma_load_2d_2sm_addr(sb, tb, fb, kb * BK, b_c);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -125,39 +136,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // =========================== MMA issuer (leader CTA only) ===========================
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM2, BN, false, B_MN);
-      const uint32_t b_lbo = B_MN ? 64 * BK * 2 : 16;
-      const uint32_t b_kadv = B_MN ? 16 * 128 : 32;
+      constexpr uint32_t b_lbo = B_MN ? 64 * BK * 2 : 16;
+      constexpr uint32_t b_kadv = (B_MN ? 16 * 128 : 32) >> 4;
+      const uint64_t da0 = make_smem_desc(smem_base, 16, 1024);
+      const uint64_t db0 = make_smem_desc(smem_base + A_STAGE_BYTES, b_lbo, 1024);
+      const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
       TileSched sched;
       sched.init(p, n_tiles, BM2);
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int t = cluster_id;; t += n_clusters, ++it) {
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_addr(tempty0 + as * 8, aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_addr(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = da0 + stage * (STAGE_BYTES >> 4);
+          const uint64_t db = db0 + stage * (STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
-            uint64_t db = make_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-            umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
-          }
-          umma_commit_2sm(&empty_bar[stage]);
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d_tmem, da + k * 2, db + k * b_kadv, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2sm_addr(empty0 + stage * 8);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull_bar[as]);
+        umma_commit_2sm_addr(tfull0 + as * 8);
       }
     }
   } else {

@@ -107,6 +107,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     if (elect_one()) {  // elect.sync: ptxas keeps the single-thread body on the uniform datapath
       constexpr uint32_t idesc = make_idesc_bf16(BM, WG_BN, true, true);  // both operands MN-major
+      const uint64_t dA0 = make_smem_desc(smem_u32(smem), 8192, 1024);    // stage 0, k-step 0; later ones are + (bytes >> 4)
+      const uint64_t dB0 = make_smem_desc(smem_u32(smem) + 64 * BM * 2, 8192, 1024);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
@@ -124,13 +126,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int s = 0; s < slabs; ++s) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
-            const uint32_t sb = sa + 64 * BM * 2;
+            const uint64_t da = dA0 + stage * (WG_STAGE_BYTES >> 4), db = dB0 + stage * (WG_STAGE_BYTES >> 4);
             const int kmax = min(4, ksteps - s * 4);
             for (int k = 0; k < kmax; ++k) {
-              const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
-              const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
-              umma_bf16_ss(d_tmem, da, db, idesc, started);
+              umma_bf16_ss(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc, started);
               started = 1;
             }
             umma_commit(&empty_bar[stage]);
@@ -284,6 +283,8 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, WG2_BN, true, true);
+      const uint64_t dA0 = make_smem_desc(smem_u32(smem), 8192, 1024);
+      const uint64_t dB0 = make_smem_desc(smem_u32(smem) + 64 * BM * 2, 8192, 1024);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total; t += n_clusters, ++it) {
@@ -301,12 +302,10 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int s = 0; s < slabs; ++s) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * WG2_STAGE_BYTES);
-            const uint32_t sb = sa + 64 * BM * 2;
+            const uint64_t da = dA0 + stage * (WG2_STAGE_BYTES >> 4), db = dB0 + stage * (WG2_STAGE_BYTES >> 4);
             const int kmax = min(4, ksteps - s * 4);
             for (int k = 0; k < kmax; ++k) {
-              umma_bf16_ss_2sm(d_tmem, make_smem_desc(sa + k * 2048, 8192, 1024), make_smem_desc(sb + k * 2048, 8192, 1024),
-                               idesc, started);
+              umma_bf16_ss_2sm(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc, started);
               started = 1;
             }
             umma_commit_2sm(&empty_bar[stage]);

@@ -69,7 +69,39 @@ ARIA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Address-form variants (shared-memory addresses as plain 32-bit values) for the single-thread issue loops, where every
+// generic->shared conversion and pointer add is latency on the critical path.
+ARIA_DEVICE void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 0xFFF) == 0xFFF) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) {
+        printf("aria_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+        __trap();
+      }
+    }
+  }
+}
+ARIA_DEVICE void mbar_arrive_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
+ARIA_DEVICE void tma_load_2d_addr(uint32_t dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 ARIA_DEVICE void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -193,6 +225,13 @@ ARIA_DEVICE void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// address form: `leader_bar_addr` already has the peer bit cleared
+ARIA_DEVICE void tma_load_2d_2sm_addr(uint32_t dst, const CUtensorMap* m, uint32_t leader_bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 ARIA_DEVICE void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols) : "memory");
@@ -218,6 +257,17 @@ ARIA_DEVICE void umma_commit_2sm(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+ARIA_DEVICE void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
+ARIA_DEVICE void umma_commit_2sm_addr(uint32_t bar_addr) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar_addr), "h"(mask) : "memory");
 }
 
 // ---------------------------------------------------------------- UMMA descriptors
