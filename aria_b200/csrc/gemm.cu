@@ -338,8 +338,12 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     const bool divisible = swiglu ? (d->n % 128 == 0) : ((d->n_seg == 1 && !b_gnk) || d->n % 256 == 0);
     const int64_t m_tiles256 = (d->num_groups == 1) ? (d->m + 255) / 256 : (d->m / 256 + d->num_groups / 2);
     const int64_t tiles256 = m_tiles256 * ((n_out_total + out_bn256 - 1) / out_bn256);
+    static const int mid = [] { const char* e = getenv("ARIA_GEMM_MID"); return e ? atoi(e) : 0; }();
     if (divisible && tiles256 * 10 >= 13 * (sm_count() / 2)) {
       BN = 256;
+    } else if (mid && d->num_groups == 1 && d->m >= 256) {
+      // mid-size dense GEMM (e.g. the T=768 LM projections): 256 x 128 pair tiles pull 24 KB per CTA per k-block from
+      // L2 instead of 32 KB (ARIA_GEMM_MID=1, A/B switch)
     } else {
       two_cta = false;
     }
