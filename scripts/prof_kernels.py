@@ -1,5 +1,5 @@
 """Tiny drivers for ncu captures: `attn` (ViT-shape attention), `attn_causal`, `fc1` (cfg-2 fc1 grouped GEMM + SwiGLU),
-`fc2`, `dense` (ViT fc1 GEMM with gelu)."""
+`fc2`, `dense` (ViT fc1 GEMM with gelu), `dense_big` (8192^3 on the 2-CTA kernel)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -62,4 +62,9 @@ elif mode == "dense":
     b = torch.randn(4304, device=dev).bfloat16()
     for _ in range(3):
         ops.linear(x, w, b, act=L.ACT_GELU_TANH)
+elif mode == "dense_big":
+    x = torch.randn(8192, 8192, device=dev).bfloat16()
+    w = (torch.randn(8192, 8192, device=dev) * 0.02).bfloat16()
+    for _ in range(3):
+        ops.linear(x, w)
 torch.cuda.synchronize()
