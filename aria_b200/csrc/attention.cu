@@ -455,12 +455,8 @@ extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, v
   p.causal = causal;
   p.key_mask = key_mask;
   p.out = static_cast<__nv_bfloat16*>(out);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM) != cudaSuccess)
-      return ARIA_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (ensure_dynamic_smem(attr_set, attn_fwd2_kernel, A2_SMEM) != cudaSuccess) return ARIA_ERR_CUDA;
   p.n_q_tiles = (Tq + 2 * AT_BM - 1) / (2 * AT_BM);  // 256-row query pairs
   const int64_t grid = static_cast<int64_t>(B) * H * p.n_q_tiles;
   ARIA_CHECK_ARG(grid < (1ll << 31));

@@ -81,15 +81,33 @@ inline int make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64
   return make_tmap_bf16(tm, ptr, 2, dims, str, box);
 }
 
+// Per-device state: one process may drive several GPUs (the reference's device_map="auto", aria/inference.py:55-57), and
+// both the SM count and cudaFuncSetAttribute opt-ins belong to the CURRENT device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+// `flags` is a function-local `static bool flags[kMaxDevices]`: true once the dynamic-smem opt-in was done on that device.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(bool* flags, Kernel kern, int bytes) {
+  const int dev = current_device();
+  if (flags[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) flags[dev] = true;
+  else fprintf(stderr, "aria_b200: cudaFuncSetAttribute(smem=%d) failed: %s\n", bytes, cudaGetErrorString(e));
+  return e;
 }
 
 }  // namespace aria

@@ -217,15 +217,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap* tmB, const Gem
   // + (128-AM) rows of slack: the M=128 MMA of the last stage reads 16 KB from a stage base whose A part is only AM rows
   constexpr int SMEM = STAGES * (AM * BK * 2 + B_STAGE_BYTES) + 1024 /*align*/ + 512 /*barriers*/ + (BM - AM) * BK * 2;
   auto kern = gemm_kernel<BN, B_MN, EPI, AM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) {
-      fprintf(stderr, "aria_b200: cudaFuncSetAttribute(smem=%d) failed: %s\n", SMEM, cudaGetErrorString(e));
-      return ARIA_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (ensure_dynamic_smem(attr_set, kern, SMEM) != cudaSuccess) return ARIA_ERR_CUDA;
   int grid = sm_count();
   if (max_tiles < grid) grid = max_tiles;
   if (grid < 1) grid = 1;

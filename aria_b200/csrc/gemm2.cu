@@ -207,15 +207,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap* tmB, const Ge
   constexpr int STAGES = (BN == 256) ? 6 : 8;
   constexpr int SMEM = STAGES * (A_STAGE_BYTES + BH * BK * 2) + 1024 + 256;
   auto kern = gemm2_kernel<BN, B_MN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) {
-      fprintf(stderr, "aria_b200: cudaFuncSetAttribute(smem=%d) failed: %s\n", SMEM, cudaGetErrorString(e));
-      return ARIA_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (ensure_dynamic_smem(attr_set, kern, SMEM) != cudaSuccess) return ARIA_ERR_CUDA;
   int clusters = sm_count() / 2;
   if (max_tiles < clusters) clusters = max_tiles;
   if (clusters < 1) clusters = 1;

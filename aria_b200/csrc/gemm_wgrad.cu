@@ -394,12 +394,9 @@ extern "C" int aria_grouped_wgrad(const void* a, int64_t lda, const void* b, int
   p.out = static_cast<__nv_bfloat16*>(out);
   constexpr int SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
   constexpr int SMEM2 = WG_STAGES * WG2_STAGE_BYTES + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return ARIA_ERR_CUDA;
-    if (cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) != cudaSuccess) return ARIA_ERR_CUDA;
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {}, attr_set2[kMaxDevices] = {};
+  if (ensure_dynamic_smem(attr_set, wgrad_kernel, SMEM) != cudaSuccess) return ARIA_ERR_CUDA;
+  if (ensure_dynamic_smem(attr_set2, wgrad2_kernel, SMEM2) != cudaSuccess) return ARIA_ERR_CUDA;
   {  // 2-CTA pairs when there are enough 256 x 256 output tiles to fill them (the large expert / MLP weight matrices)
     const int64_t tiles2 = static_cast<int64_t>(num_groups) * ((md + 2 * BM - 1) / (2 * BM)) * ((nd + WG2_BN - 1) / WG2_BN);
     static int force = -1;

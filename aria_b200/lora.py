@@ -1,0 +1,125 @@
+"""LoRA on the grouped expert GEMMs — mirror of the reference's `GroupedGemmLoraLayer`
+(aria/lora/layers.py:30-152, mapped onto every `GroupedGEMM` by peft at aria/train.py:107):
+
+    result = base_layer(x, tokens_per_expert) + lora_B(lora_A(x, tpe), tpe) * (lora_alpha / r)          (layers.py:132-140)
+
+with `lora_A = GroupedGEMM(in, r, groups)` and `lora_B = GroupedGEMM(r, out, groups)` (layers.py:87-92), i.e. parameters
+`lora_A.<adapter>.weight [E, in, r]` and `lora_B.<adapter>.weight [E, r, out]` in the reference's layout.
+
+B200 mapping: r (8 in recipes/config_lora.yaml) is far below a tensor-core tile, so both adapters are zero-padded to
+R_PAD = 128 columns / rows in a per-step working copy and run through the same tcgen05 grouped-GEMM kernels as the experts
+(padded lanes multiply zeros: exact).  The scaling is folded into the padded A copy (exact for the usual power-of-two
+alpha/r; one bf16 rounding otherwise) and the `+ base` is the residual input of the B GEMM's epilogue, so the adapter
+costs two extra launches forward.  Backward (adapters and input only; the base weight is frozen as in the recipe):
+
+    dB = (x A s)^T dy      `aria_grouped_wgrad`          dh = dy B^T          `aria_gemm` B_GNK (weight read transposed)
+    dA = s * x^T dh        `aria_grouped_wgrad`          dx = dy W^T + dh (A s)^T
+
+Group rows must start on multiples of 16 (the training dispatcher's `row_align=16`), as for every wgrad here.
+Parity: the reference layer needs `peft` (absent offline), so this piece is checked against the oracle's restatement only.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .moe_lm import GroupedGEMM, _as_offsets
+
+R_PAD = 128
+
+
+def _pad_a(a: torch.Tensor, scale: float) -> torch.Tensor:
+    """[E, in, r] -> [E, in, R_PAD] * scale (bf16)."""
+    E, K, r = a.shape
+    out = torch.zeros((E, K, R_PAD), dtype=a.dtype, device=a.device)
+    out[:, :, :r] = a * scale if scale != 1.0 else a
+    return out
+
+
+def _pad_b(b: torch.Tensor) -> torch.Tensor:
+    """[E, r, out] -> [E, R_PAD, out]."""
+    E, r, N = b.shape
+    out = torch.zeros((E, R_PAD, N), dtype=b.dtype, device=b.device)
+    out[:, :r] = b
+    return out
+
+
+class _LoraGroupedGemm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, a, b, offsets, scale: float):
+        a_pad, b_pad = _pad_a(a.detach(), scale), _pad_b(b.detach())
+        base = ops.grouped_gemm(x, w, offsets)
+        h = ops.grouped_gemm(x, a_pad, offsets)                     # [rows, R_PAD] = x A s
+        out = ops.grouped_gemm(h, b_pad, offsets, residual=base)    # base + h B
+        ctx.save_for_backward(x, w, a_pad, b_pad, h, offsets)
+        ctx.scale, ctx.r = scale, a.shape[2]
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, a_pad, b_pad, h, offsets = ctx.saved_tensors
+        dy = dy.contiguous()
+        r = ctx.r
+        d_b = ops.grouped_wgrad(h, dy, offsets)[:, :r].contiguous()             # [E, r, out]
+        dh = ops.grouped_gemm_nt(dy, b_pad, offsets)                            # dy @ B_pad[e].T -> [rows, R_PAD]
+        d_a = ops.grouped_wgrad(x, dh, offsets)[:, :, :r]                       # x^T dh (d/dA of x (A s) is s x^T dh)
+        d_a = (d_a * ctx.scale).contiguous() if ctx.scale != 1.0 else d_a.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.grouped_gemm_nt(dy, w, offsets)                            # base path: dy @ W[e].T
+            dx = ops.grouped_gemm_nt(dh, a_pad, offsets, residual=dx)           # + adapter path: dh @ (A s)[e].T
+        return dx, None, d_a, d_b, None, None
+
+
+class GroupedGemmLoraLayer(nn.Module):
+    """Same attribute names as the reference layer (`base_layer`, `lora_A`, `lora_B`, `scaling`, `r`, `lora_alpha`), one
+    adapter per name; dropout is the identity (lora_dropout 0 in the recipe; a non-zero value is rejected)."""
+
+    def __init__(self, base_layer: GroupedGEMM, adapter_name: str = "default", r: int = 8, lora_alpha: int = 32,
+                 lora_dropout: float = 0.0):
+        super().__init__()
+        if r <= 0:
+            raise ValueError(f"`r` should be a positive integer value but the value passed is {r}")   # layers.py:74-77
+        if r > R_PAD or r % 8:
+            raise ValueError(f"r must be a multiple of 8 and <= {R_PAD} on this path, got {r}")
+        if lora_dropout:
+            raise ValueError("lora_dropout > 0 is not supported on the B200 path")
+        self.base_layer = base_layer
+        self.in_features, self.out_features, self.groups = base_layer.in_features, base_layer.out_features, base_layer.groups
+        dev = base_layer.weight.device
+        self.r = {adapter_name: r}
+        self.lora_alpha = {adapter_name: lora_alpha}
+        self.scaling = {adapter_name: lora_alpha / r}
+        self.lora_A = nn.ModuleDict({adapter_name: GroupedGEMM(self.in_features, r, self.groups, device=dev)})
+        self.lora_B = nn.ModuleDict({adapter_name: GroupedGEMM(r, self.out_features, self.groups, device=dev)})
+        self.active_adapters = [adapter_name]
+        self.disable_adapters = False
+        for m in (self.lora_A[adapter_name], self.lora_B[adapter_name]):
+            m.weight.requires_grad_(True)
+        self.reset_lora_parameters(adapter_name)
+
+    def reset_lora_parameters(self, adapter_name: str):
+        """peft's default for linear-like layers: A ~ kaiming-uniform, B = 0 (the adapter starts as a no-op)."""
+        a, b = self.lora_A[adapter_name].weight, self.lora_B[adapter_name].weight
+        with torch.no_grad():
+            bound = (6.0 / ((1 + 5.0) * self.in_features)) ** 0.5
+            a.uniform_(-bound, bound)
+            b.zero_()
+
+    def forward(self, x: torch.Tensor, tokens_per_expert: torch.Tensor) -> torch.Tensor:
+        off = _as_offsets(tokens_per_expert, self.groups, x.device)
+        if self.disable_adapters:
+            return ops.grouped_gemm(x, self.base_layer.weight, off)
+        result = None
+        for name in self.active_adapters:
+            if name not in self.lora_A:
+                continue
+            a, b = self.lora_A[name].weight, self.lora_B[name].weight
+            if result is None:
+                result = _LoraGroupedGemm.apply(x, self.base_layer.weight, a, b, off, float(self.scaling[name]))
+            else:  # the reference loops over active adapters (layers.py:125-140); one adapter per layer is what its recipe uses
+                raise NotImplementedError("more than one active adapter per layer")
+        if result is None:
+            result = ops.grouped_gemm(x, self.base_layer.weight, off)
+        return result

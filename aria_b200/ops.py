@@ -106,8 +106,8 @@ def linear_swiglu(x: torch.Tensor, gate_w: torch.Tensor, up_w: torch.Tensor) -> 
 
 
 def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu: bool = False,
-                 dbg=(0, 0, 0), group_mod: int = 0) -> torch.Tensor:
-    """out[off[e]:off[e+1]] = a[off[e]:off[e+1]] @ b[e]; b [E, K, N] (GroupedGEMM.weight, moe_lm.py:465).
+                 dbg=(0, 0, 0), group_mod: int = 0, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[off[e]:off[e+1]] = a[off[e]:off[e+1]] @ b[e] (+ residual); b [E, K, N] (GroupedGEMM.weight, moe_lm.py:465).
     swiglu=True fuses `glu` (moe_lm.py:505-507): b has 2I columns, out has I."""
     _chk(a), _chk(b), _chk(offsets, torch.int32)
     rows, K = a.shape
@@ -124,14 +124,19 @@ def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu
     d.group_offsets = offsets.data_ptr()
     d.epilogue = L.EPI_SWIGLU if swiglu else L.EPI_LINEAR
     d.out[0], d.ldo = out.data_ptr(), N
+    if residual is not None:
+        assert not swiglu and residual.shape == out.shape
+        _chk(residual)
+        d.residual, d.ldr = residual.data_ptr(), N
     d.dbg_lbo, d.dbg_sbo, d.dbg_kadv = dbg
     _run_gemm(d, a, "grouped_gemm")
     return out
 
 
-def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, group_mod: int = 0) -> torch.Tensor:
-    """Data-gradient of the grouped GEMM: out[rows of e] = a[rows of e] @ b[e].T with b [E, N_out, K] (K contiguous) —
-    i.e. the forward weight [E, in, out] used transposed, read in place (ARIA_B_GNK)."""
+def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, group_mod: int = 0,
+                    residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data-gradient of the grouped GEMM: out[rows of e] = a[rows of e] @ b[e].T (+ residual) with b [E, N_out, K]
+    (K contiguous) — i.e. the forward weight [E, in, out] used transposed, read in place (ARIA_B_GNK)."""
     _chk(a), _chk(b), _chk(offsets, torch.int32)
     rows, K = a.shape
     E, N, Kb = b.shape
@@ -146,6 +151,10 @@ def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, gro
     d.group_offsets = offsets.data_ptr()
     d.epilogue = L.EPI_LINEAR
     d.out[0], d.ldo = out.data_ptr(), N
+    if residual is not None:
+        assert residual.shape == out.shape
+        _chk(residual)
+        d.residual, d.ldr = residual.data_ptr(), N
     _run_gemm(d, a, "grouped_gemm_nt")
     return out
 

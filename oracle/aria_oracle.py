@@ -126,6 +126,15 @@ def sequential_gemm(inp: Tensor, weight: Tensor, counts: Tensor) -> Tensor:
     return out
 
 
+def grouped_gemm_lora(x: Tensor, w: Tensor, lora_a: Tensor, lora_b: Tensor, counts: Tensor, scaling: float) -> Tensor:
+    """aria/lora/layers.py:125-140 `GroupedGemmLoraLayer.forward` (one active adapter, dropout = identity, no DoRA):
+    result = base_layer(x, tpe) + lora_B(lora_A(x, tpe), tpe) * scaling, where lora_A / lora_B are `GroupedGEMM`s
+    (layers.py:87-92) with weights [E, in, r] / [E, r, out].  NOT pinned to a live reference run: the layer needs
+    `peft`, which is absent offline; the arithmetic is the reference's own `sequential_gemm` applied three times."""
+    result = sequential_gemm(x, w, counts)
+    return result + sequential_gemm(sequential_gemm(x, lora_a, counts), lora_b, counts) * scaling
+
+
 def glu(x: Tensor) -> Tensor:
     """moe_lm.py:505-507: first half is the gate (silu), second half the up projection."""
     a, b = torch.chunk(x, 2, dim=-1)

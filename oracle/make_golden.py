@@ -110,6 +110,44 @@ def main():
                         combined=comb, shared=shared, out=out, checksum=C.state_checksum(sd), seed=1),
                    os.path.join(OUT, f"moe_layer_cfg1_{tag}.pt"))
 
+    # ---- (1b) training-mode routing: the same layer in .train(), forward + backward with the z-loss / load-balancing loss
+    # side effects (moe_lm.py:84-166, 203-241) and a non-unit MoEAuxLossAutoScaler scale; reference gradients are the golden
+    for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        gen = torch.Generator().manual_seed(3)
+        ttc = dict(hidden_size=128, moe_num_experts=8, moe_topk=2, moe_intermediate_size=64, moe_num_shared_experts=2)
+        sd = C.moe_layer_state(ttc, gen)                    # small layer: the fixture stores every parameter gradient
+        sd["router.weight"] = sd["router.weight"] * 20      # spread the logits so the loss terms are well above rounding noise
+        x = torch.randn(2, 16, 128, generator=gen)
+        dout = torch.randn(2, 16, 128, generator=gen)
+        sd = {k: v.to(dtype) for k, v in sd.items()}
+        x, dout = x.to(dtype), dout.to(dtype)
+        z_c, aux_c, scale = 0.5, 2.0, 8.0
+        tcfg = ref.moe_lm.AriaMoELMConfig(moe_z_loss_coeff=z_c, moe_aux_loss_coeff=aux_c, **ttc)
+        with torch.enable_grad():
+            layer = ref.moe_lm.MoELayer(tcfg)
+            layer.load_state_dict(sd, strict=True)
+            layer = layer.to(dtype).train()
+            ref.moe_lm.MoEAuxLossAutoScaler.set_loss_scale(torch.tensor(scale))
+            try:
+                xr = x.clone().requires_grad_(True)
+                out = layer(xr)
+                out.backward(dout)
+            finally:
+                ref.moe_lm.MoEAuxLossAutoScaler.set_loss_scale(torch.tensor(1.0))
+            grads = {n: p.grad.detach().clone() for n, p in layer.named_parameters()}
+            w = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+            xo = x.clone().requires_grad_(True)
+            O._LossGradInjector.scale = scale
+            try:
+                O.moe_layer(xo, w, 2, loss_coeffs=(z_c, aux_c)).backward(dout)
+            finally:
+                O._LossGradInjector.scale = 1.0
+        err = max(float((grads[n].float() - w[n].grad.float()).abs().max()) for n in grads)
+        report.append(f"moe_layer train-mode grads {tag}: oracle-vs-reference max abs err over parameter grads {err:.3e}")
+        torch.save(dict(x=x, dout=dout, out=out.detach(), grads=grads, dx=xr.grad.detach(), z_coeff=z_c, aux_coeff=aux_c,
+                        loss_scale=scale, checksum=C.state_checksum(sd), seed=3, text_config=ttc),
+                   os.path.join(OUT, f"moe_layer_train_{tag}.pt"))
+
     # ---- (2) tiny full model: ViT + projector + merge + 2-layer MoE LM ----
     for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
         sd = C.aria_state(cfg, seed=0, dtype=dtype)

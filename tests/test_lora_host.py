@@ -1,0 +1,37 @@
+"""CPU: host-side contract of the LoRA mirror (aria/lora/layers.py:30-152) — parameter names/shapes as peft saves them,
+argument validation, and that there is no CPU fallback."""
+import pytest
+import torch
+
+from aria_b200 import lora, moe_lm
+
+
+def test_lora_layer_state_dict_layout_and_init():
+    base = moe_lm.GroupedGEMM(64, 96, 4)
+    layer = lora.GroupedGemmLoraLayer(base, "default", r=8, lora_alpha=32)
+    sd = layer.state_dict()
+    assert set(sd) == {"base_layer.weight", "lora_A.default.weight", "lora_B.default.weight"}
+    assert sd["lora_A.default.weight"].shape == (4, 64, 8)       # GroupedGEMM(in, r, groups).weight  (layers.py:87-89)
+    assert sd["lora_B.default.weight"].shape == (4, 8, 96)       # GroupedGEMM(r, out, groups).weight (layers.py:90-92)
+    assert layer.scaling["default"] == 4.0                        # lora_alpha / r (layers.py:93)
+    assert float(sd["lora_B.default.weight"].float().abs().max()) == 0.0
+    assert float(sd["lora_A.default.weight"].float().abs().max()) > 0.0
+    trainable = {n for n, p in layer.named_parameters() if p.requires_grad}
+    assert trainable == {"lora_A.default.weight", "lora_B.default.weight"}
+
+
+def test_lora_layer_rejects_bad_arguments():
+    base = moe_lm.GroupedGEMM(64, 96, 4)
+    with pytest.raises(ValueError):   # same message as the reference (layers.py:74-77)
+        lora.GroupedGemmLoraLayer(base, r=0)
+    with pytest.raises(ValueError):
+        lora.GroupedGemmLoraLayer(base, r=12)
+    with pytest.raises(ValueError):
+        lora.GroupedGemmLoraLayer(base, r=8, lora_dropout=0.1)
+
+
+def test_lora_layer_has_no_cpu_path():
+    base = moe_lm.GroupedGEMM(64, 96, 4)
+    layer = lora.GroupedGemmLoraLayer(base, r=8)
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(16, 64, dtype=torch.bfloat16), torch.tensor([16, 0, 0, 0]))

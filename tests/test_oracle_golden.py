@@ -38,6 +38,39 @@ def test_moe_layer_cfg1(tag, dtype, tol):
     assert (out.float() - g["out"].float()).abs().max() <= tol * 10
 
 
+@pytest.mark.parametrize("tag,dtype,tol", [("fp32", torch.float32, 1e-6), ("bf16", torch.bfloat16, 0.0)])
+def test_moe_layer_training_mode_gradients(tag, dtype, tol):
+    """Training-mode routing (z-loss + load-balancing loss through MoEAuxLossAutoScaler, moe_lm.py:84-166, 203-241, with a
+    loss scale of 8): every parameter gradient of the unmodified reference, captured by oracle/make_golden.py."""
+    g = _load(f"moe_layer_train_{tag}.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    sd = C.moe_layer_state(g["text_config"], gen)
+    sd["router.weight"] = sd["router.weight"] * 20
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    assert C.state_checksum(sd) == pytest.approx(g["checksum"], rel=1e-9), "seeded weights drifted"
+    w = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+    x = g["x"].clone().requires_grad_(True)
+    O._LossGradInjector.scale = g["loss_scale"]
+    try:
+        with torch.enable_grad():
+            out = O.moe_layer(x, w, g["text_config"]["moe_topk"], loss_coeffs=(g["z_coeff"], g["aux_coeff"]))
+            out.backward(g["dout"])
+    finally:
+        O._LossGradInjector.scale = 1.0
+    assert (out.detach().float() - g["out"].float()).abs().max() <= tol * 10
+    for n, want in g["grads"].items():
+        scale = max(1.0, float(want.float().abs().max()))
+        assert (w[n].grad.float() - want.float()).abs().max() <= tol * scale, n
+    # dx sums three autograd branches; bf16 accumulation order is an engine detail -> ulp-level tolerance there
+    xtol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert (x.grad.float() - g["dx"].float()).abs().max() <= xtol * max(1.0, float(g["dx"].float().abs().max()))
+    # the losses really contribute: the router gradient differs from the eval-mode one
+    w0 = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+    with torch.enable_grad():
+        O.moe_layer(g["x"].clone(), w0, g["text_config"]["moe_topk"]).backward(g["dout"])
+    assert (w0["router.weight"].grad.float() - g["grads"]["router.weight"].float()).abs().max() > 1e-3
+
+
 @pytest.mark.parametrize("tag,dtype,tol", [("fp32", torch.float32, 5e-6), ("bf16", torch.bfloat16, 0.0)])
 @pytest.mark.parametrize("masked", ["full", "masked"])
 def test_aria_tiny_forward(tag, dtype, tol, masked):
