@@ -8,8 +8,9 @@ Seams:
   3. decoder-layer attention (moe_lm.py:594)                -> `AriaAttention`-style forward on the module's own q/k/v/o_proj
   4. `Idefics2EncoderLayer.forward` (vision_encoder.py:120) -> fused ViT layer
 
-Only (1) and (2) are wired by `install()`; (3)/(4) need the HF cache / mask plumbing of the host transformers version and
-are exposed as the standalone mirrors in `aria_b200.moe_lm` / `aria_b200.vision_encoder` (load the same state dict).
+(1) and (2) are wired by `install()`; (3) is `aria_b200.hf_attention.register()` (an implementation key for transformers'
+attention interface — the module keeps its projections, RoPE and HF Cache); (4) needs the mask plumbing of the host
+transformers version and is exposed as the standalone mirror in `aria_b200.vision_encoder` (load the same state dict).
 There is no CPU fallback: the patched modules require CUDA bf16 tensors.
 """
 from __future__ import annotations
