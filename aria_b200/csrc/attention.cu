@@ -28,8 +28,9 @@ constexpr int AT_HALF = AT_TILE / 2;       // one SW128 atom column: [128 rows][
 
 ARIA_DEVICE float fast_exp2(float x) { return fast_ex2(x); }
 
-// (A polynomial exp2 on the FMA pipes for a quarter of the elements — the FA4 trick — was measured and LOST 20 %: this
-// softmax is issue-slot bound, not MUFU bound; see profiles/r01_attention_notes.txt.)
+// (A polynomial exp2 on the FMA pipes for a quarter of the elements — the FA4 trick — was measured and LOST 20 %.  That
+// measurement predates the lean MMA-issue loop: at the time the issuing thread, not the softmax, set the pace, so the
+// trick only added instructions.  To be re-measured; see profiles/r01_attention_notes.txt.)
 struct AttnParams {
   int B, H, Tq, Tk;
   int out_hd;
