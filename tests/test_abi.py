@@ -63,6 +63,16 @@ def test_bad_arguments_are_errors_not_crashes(lib):
     assert lib.aria_route_from_logits(None, None, None, None, 4, 8, 2, None) == -1
     assert lib.aria_permute_rows(None, None, None, 4, 256, None) == -1
     assert lib.aria_attention_decode_workspace_bytes(32, 20, 2048) == 32 * 20 * 8 * 130 * 4
+    # training-mode router losses: null pointers and more experts than one warp pass covers (E <= 256) are rejected
+    assert lib.aria_router_aux_bwd(None, None, None, 4, 8, 2, 0.1, 0.1, 1.0, None) == -1
+    fake = ctypes.c_void_p(0x1000)   # never dereferenced: validation fails first
+    assert lib.aria_router_aux_bwd(fake, fake, fake, 4, 300, 2, 0.1, 0.1, 1.0, None) == -1
+    assert lib.aria_router_aux_loss(fake, fake, fake, 4, 8, 2, 0.1, 0.1, fake, 0, None) == -1   # workspace too small
+    assert lib.aria_router_aux_workspace_bytes(64) % (65 * 4) == 0
+    # GEMM descriptor validation: n must be a multiple of 8 (16-byte rows)
+    d.a = d.b[0] = d.out[0] = 0x1000
+    d.m, d.n, d.k, d.lda, d.n_seg, d.num_groups = 16, 12, 64, 64, 1, 1
+    assert lib.aria_gemm(ctypes.byref(d), None) == -1
 
 
 def test_no_cpu_fallback():
