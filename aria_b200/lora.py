@@ -16,7 +16,9 @@ costs two extra launches forward.  Backward (adapters and input only; the base w
     dA = s * x^T dh        `aria_grouped_wgrad`          dx = dy W^T + dh (A s)^T
 
 Group rows must start on multiples of 16 (the training dispatcher's `row_align=16`), as for every wgrad here.
-Parity: the reference layer needs `peft` (absent offline), so this piece is checked against the oracle's restatement only.
+Parity: the oracle's restatement is pinned bit-exactly to the unmodified reference layer, loaded under a stand-in for the two
+peft symbols it imports (oracle/ref_loader.py `load_reference_lora`, tests/test_oracle_vs_reference.py) and through
+tests/golden/lora_grouped_gemm_*.pt on the GPU box.
 """
 from __future__ import annotations
 
@@ -95,6 +97,7 @@ class GroupedGemmLoraLayer(nn.Module):
         self.lora_B = nn.ModuleDict({adapter_name: GroupedGEMM(r, self.out_features, self.groups, device=dev)})
         self.active_adapters = [adapter_name]
         self.disable_adapters = False
+        self.merged_adapters = []
         for m in (self.lora_A[adapter_name], self.lora_B[adapter_name]):
             m.weight.requires_grad_(True)
         self.reset_lora_parameters(adapter_name)
@@ -107,10 +110,36 @@ class GroupedGemmLoraLayer(nn.Module):
             a.uniform_(-bound, bound)
             b.zero_()
 
+    @property
+    def merged(self) -> bool:
+        return bool(self.merged_adapters)
+
+    def get_delta_weight(self, adapter: str) -> torch.Tensor:
+        """layers.py:193-228: A @ B * scaling, [E, in, out] (a one-off merge-time product, not on the hot path)."""
+        return torch.matmul(self.lora_A[adapter].weight, self.lora_B[adapter].weight) * self.scaling[adapter]
+
+    def merge(self, adapter_names=None) -> None:
+        """layers.py:154-191: fold the active adapters into the base weight (W += A B s); forward then runs the plain GEMM."""
+        for name in (adapter_names or self.active_adapters):
+            if name in self.lora_A and name not in self.merged_adapters:
+                with torch.no_grad():
+                    self.base_layer.weight.data += self.get_delta_weight(name)
+                self.merged_adapters.append(name)
+
+    def unmerge(self) -> None:
+        while self.merged_adapters:
+            name = self.merged_adapters.pop()
+            with torch.no_grad():
+                self.base_layer.weight.data -= self.get_delta_weight(name)
+
     def forward(self, x: torch.Tensor, tokens_per_expert: torch.Tensor) -> torch.Tensor:
         off = _as_offsets(tokens_per_expert, self.groups, x.device)
         if self.disable_adapters:
+            if self.merged:
+                self.unmerge()                                         # layers.py:113-116
             return ops.grouped_gemm(x, self.base_layer.weight, off)
+        if self.merged:
+            return ops.grouped_gemm(x, self.base_layer.weight, off)    # layers.py:121-122
         result = None
         for name in self.active_adapters:
             if name not in self.lora_A:

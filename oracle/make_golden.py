@@ -148,6 +148,37 @@ def main():
                         loss_scale=scale, checksum=C.state_checksum(sd), seed=3, text_config=ttc),
                    os.path.join(OUT, f"moe_layer_train_{tag}.pt"))
 
+    # ---- (1c) LoRA on the grouped expert GEMM: the unmodified aria/lora/layers.py under the peft stand-in of ref_loader ----
+    from oracle.ref_loader import load_reference_lora
+    lora_mod = load_reference_lora()
+    for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        gen = torch.Generator().manual_seed(4)
+        E, K, N, r, alpha = 4, 128, 192, 8, 32
+        counts = torch.tensor([32, 0, 80, 16])                        # 16-row aligned groups, one empty
+        rows = int(counts.sum())
+        w = (torch.randn(E, K, N, generator=gen) * 0.05).to(dtype)
+        a = (torch.randn(E, K, r, generator=gen) * 0.05).to(dtype)
+        b = (torch.randn(E, r, N, generator=gen) * 0.05).to(dtype)
+        x = torch.randn(rows, K, generator=gen).to(dtype)
+        dy = torch.randn(rows, N, generator=gen).to(dtype)
+        with torch.enable_grad():
+            base = ref.moe_lm.GroupedGEMM(K, N, E)
+            layer = lora_mod.GroupedGemmLoraLayer(base, "default", r=r, lora_alpha=alpha).to(dtype)
+            with torch.no_grad():
+                base.weight.copy_(w)
+                layer.lora_A["default"].weight.copy_(a)
+                layer.lora_B["default"].weight.copy_(b)
+            xr = x.clone().requires_grad_(True)
+            out = layer(xr, counts)
+            out.backward(dy)
+        o_out = O.grouped_gemm_lora(x, w, a, b, counts, alpha / r)
+        err = float((out.detach().float() - o_out.float()).abs().max())
+        report.append(f"lora grouped gemm {tag}: oracle-vs-reference max abs err {err:.3e}")
+        torch.save(dict(x=x, dy=dy, w=w, a=a, b=b, counts=counts, r=r, lora_alpha=alpha, out=out.detach(),
+                        d_a=layer.lora_A["default"].weight.grad.detach(), d_b=layer.lora_B["default"].weight.grad.detach(),
+                        dx=xr.grad.detach()),
+                   os.path.join(OUT, f"lora_grouped_gemm_{tag}.pt"))
+
     # ---- (2) tiny full model: ViT + projector + merge + 2-layer MoE LM ----
     for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
         sd = C.aria_state(cfg, seed=0, dtype=dtype)

@@ -75,3 +75,79 @@ def load_reference():
         spec.loader.exec_module(m)
         _loaded[mod] = m
     return types.SimpleNamespace(**_loaded)
+
+
+def load_reference_lora():
+    """Loads the unmodified `aria/lora/layers.py` (GroupedGemmLoraLayer).  It subclasses peft's `LoraLayer`, and peft is not
+    installed offline, so a minimal stand-in for the two peft symbols it imports is registered first (harness code, outside
+    the reference files): just the bookkeeping `LoraLayer.__init__` / `set_adapter` / properties that the reference's
+    `__init__`, `update_layer` and `forward` (layers.py:30-152) touch.  The arithmetic under test is the reference's own."""
+    ref = load_reference()
+    if "lora_layers" in _loaded:
+        return _loaded["lora_layers"]
+    import math
+
+    from torch import nn
+
+    class LoraLayer:  # stand-in for peft.tuners.lora.LoraLayer (peft 0.13 semantics for the members used)
+        def __init__(self, base_layer, **kwargs):
+            self.base_layer = base_layer
+            self.r, self.lora_alpha, self.scaling, self.use_dora = {}, {}, {}, {}
+            self.lora_dropout = nn.ModuleDict({})
+            self.lora_A = nn.ModuleDict({})
+            self.lora_B = nn.ModuleDict({})
+            self._disable_adapters = False
+            self.merged_adapters = []
+            self.in_features, self.out_features = base_layer.in_features, base_layer.out_features
+
+        @property
+        def active_adapters(self):
+            a = self._active_adapter
+            return [a] if isinstance(a, str) else a
+
+        @property
+        def disable_adapters(self):
+            return self._disable_adapters
+
+        @property
+        def merged(self):
+            return bool(self.merged_adapters)
+
+        def get_base_layer(self):
+            return self.base_layer
+
+        def set_adapter(self, adapter_names):
+            self._active_adapter = adapter_names
+
+        def _move_adapter_to_device_of_base_layer(self, adapter_name):
+            pass
+
+        def _check_forward_args(self, x, *args, **kwargs):
+            pass
+
+        def reset_lora_parameters(self, adapter_name, init_lora_weights):
+            nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B[adapter_name].weight)
+
+    def check_adapters_to_merge(module, adapter_names=None):
+        return adapter_names if adapter_names is not None else module.active_adapters
+
+    for name, attrs in (("peft", {}), ("peft.tuners", {}), ("peft.tuners.lora", {"LoraLayer": LoraLayer}),
+                        ("peft.tuners.tuners_utils", {"check_adapters_to_merge": check_adapters_to_merge})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(sys.modules[name], k, v)
+    sys.modules["aria.model"].GroupedGEMM = ref.moe_lm.GroupedGEMM   # `from aria.model import GroupedGEMM` (layers.py:26)
+    if "aria.lora" not in sys.modules:
+        pkg = types.ModuleType("aria.lora")
+        pkg.__path__ = [os.path.join(REF_ROOT, "aria", "lora")]
+        sys.modules["aria.lora"] = pkg
+    spec = importlib.util.spec_from_file_location("aria.lora.layers", os.path.join(REF_ROOT, "aria", "lora", "layers.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["aria.lora.layers"] = m
+    spec.loader.exec_module(m)
+    _loaded["lora_layers"] = m
+    return m

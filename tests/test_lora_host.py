@@ -35,3 +35,20 @@ def test_lora_layer_has_no_cpu_path():
     layer = lora.GroupedGemmLoraLayer(base, r=8)
     with pytest.raises(RuntimeError):
         layer(torch.zeros(16, 64, dtype=torch.bfloat16), torch.tensor([16, 0, 0, 0]))
+
+
+def test_merge_and_unmerge_fold_the_adapter_into_the_base_weight():
+    """layers.py:154-228: W += A @ B * scaling; unmerge restores W (fp32 here so the round trip is exact to rounding)."""
+    base = moe_lm.GroupedGEMM(64, 96, 4)
+    layer = lora.GroupedGemmLoraLayer(base, r=8, lora_alpha=32).float()
+    with torch.no_grad():
+        base.weight.normal_(0, 0.05)
+        layer.lora_B["default"].weight.normal_(0, 0.05)
+    w0 = base.weight.detach().clone()
+    delta = torch.matmul(layer.lora_A["default"].weight, layer.lora_B["default"].weight) * 4.0
+    layer.merge()
+    assert layer.merged and torch.allclose(base.weight, w0 + delta, atol=1e-6)
+    layer.merge()                                     # idempotent
+    assert torch.allclose(base.weight, w0 + delta, atol=1e-6)
+    layer.unmerge()
+    assert not layer.merged and torch.allclose(base.weight, w0, atol=1e-6)

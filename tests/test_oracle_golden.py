@@ -71,6 +71,21 @@ def test_moe_layer_training_mode_gradients(tag, dtype, tol):
     assert (w0["router.weight"].grad.float() - g["grads"]["router.weight"].float()).abs().max() > 1e-3
 
 
+@pytest.mark.parametrize("tag,tol", [("fp32", 1e-6), ("bf16", 0.0)])
+def test_lora_grouped_gemm_golden(tag, tol):
+    """aria/lora/layers.py:125-140 forward and the adapter gradients, captured from the unmodified reference layer."""
+    g = _load(f"lora_grouped_gemm_{tag}.pt")
+    a, b, x = (g[k].clone().requires_grad_(True) for k in ("a", "b", "x"))
+    with torch.enable_grad():
+        out = O.grouped_gemm_lora(x, g["w"], a, b, g["counts"], g["lora_alpha"] / g["r"])
+        out.backward(g["dy"])
+    assert (out.detach().float() - g["out"].float()).abs().max() <= tol
+    assert (a.grad.float() - g["d_a"].float()).abs().max() <= tol * max(1.0, float(g["d_a"].float().abs().max()))
+    assert (b.grad.float() - g["d_b"].float()).abs().max() <= tol * max(1.0, float(g["d_b"].float().abs().max()))
+    xtol = 1e-6 if tag == "fp32" else 1e-2
+    assert (x.grad.float() - g["dx"].float()).abs().max() <= xtol * float(g["dx"].float().abs().max())
+
+
 @pytest.mark.parametrize("tag,dtype,tol", [("fp32", torch.float32, 5e-6), ("bf16", torch.bfloat16, 0.0)])
 @pytest.mark.parametrize("masked", ["full", "masked"])
 def test_aria_tiny_forward(tag, dtype, tol, masked):

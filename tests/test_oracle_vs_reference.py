@@ -110,3 +110,47 @@ def test_moe_layer_training_losses_backward_live(dtype, scale):
     closed = dl.t() @ x2.float()
     rel = (delta - closed).abs().max() / closed.abs().max()
     assert rel <= (1e-4 if dtype == torch.float32 else 4e-2), float(rel)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grouped_gemm_lora_layer_live(dtype):
+    """LoRA on the grouped GEMM: the unmodified `aria/lora/layers.py` (loaded under a stand-in for the two peft symbols it
+    imports, see oracle/ref_loader.py) vs the oracle's restatement — forward and the gradients of A, B and x."""
+    from oracle.ref_loader import load_reference_lora
+    ref = load_reference()
+    L = load_reference_lora()
+    g = torch.Generator().manual_seed(4)
+    E, K, N, r, alpha = 4, 64, 96, 8, 32
+    counts = torch.tensor([16, 0, 40, 24])
+    rows = int(counts.sum())
+    w = (torch.randn(E, K, N, generator=g) * 0.05).to(dtype)
+    a = (torch.randn(E, K, r, generator=g) * 0.05).to(dtype)
+    b = (torch.randn(E, r, N, generator=g) * 0.05).to(dtype)
+    x0 = torch.randn(rows, K, generator=g).to(dtype)
+    dy = torch.randn(rows, N, generator=g).to(dtype)
+    with torch.enable_grad():
+        base = ref.moe_lm.GroupedGEMM(K, N, E)
+        layer = L.GroupedGemmLoraLayer(base, "default", r=r, lora_alpha=alpha).to(dtype)
+        assert layer.scaling["default"] == alpha / r
+        with torch.no_grad():
+            base.weight.copy_(w)
+            layer.lora_A["default"].weight.copy_(a)
+            layer.lora_B["default"].weight.copy_(b)
+        xr = x0.clone().requires_grad_(True)
+        want = layer(xr, counts)
+        want.backward(dy)
+        ao, bo, xo = a.clone().requires_grad_(True), b.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        got = O.grouped_gemm_lora(xo, w, ao, bo, counts, alpha / r)
+        got.backward(dy)
+    assert torch.equal(got.detach(), want.detach())
+    assert torch.equal(ao.grad, layer.lora_A["default"].weight.grad)
+    assert torch.equal(bo.grad, layer.lora_B["default"].weight.grad)
+    tol = 1e-6 if dtype == torch.float32 else 1e-2   # dx sums two autograd branches (accumulation order, see above)
+    assert (xo.grad.float() - xr.grad.float()).abs().max() <= tol * float(xr.grad.float().abs().max())
+    # merged weights (layers.py:154-213: W += A @ B * scaling) give the same function as the adapter path
+    if dtype == torch.float32:
+        with torch.no_grad():
+            layer.merge()
+            merged = layer(x0, counts)
+        assert (merged - want.detach()).abs().max() <= 1e-5
+        assert (base.weight - (w + torch.matmul(a, b) * (alpha / r))).abs().max() <= 1e-7
