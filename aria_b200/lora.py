@@ -74,6 +74,56 @@ class _LoraGroupedGemm(torch.autograd.Function):
         return dx, None, d_a, d_b, None, None
 
 
+class _SwiGLU(torch.autograd.Function):
+    """glu of moe_lm.py:505-507 as a differentiable op over `aria_swiglu_fwd` / `aria_swiglu_bwd`."""
+
+    @staticmethod
+    def forward(ctx, h1):
+        ctx.save_for_backward(h1)
+        return ops.swiglu_fwd(h1)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (h1,) = ctx.saved_tensors
+        return ops.swiglu_bwd(h1, dh.contiguous())
+
+
+def swiglu(h1: torch.Tensor) -> torch.Tensor:
+    return _SwiGLU.apply(h1) if (torch.is_grad_enabled() and h1.requires_grad) else ops.swiglu_fwd(h1)
+
+
+def get_lora_target_modules(model_named_modules, lora_target_modules, freeze_vit=False, freeze_projector=False,
+                            freeze_llm=False, freeze_llm_layers=None):
+    """Same selection rule as the reference's `get_lora_target_modules` (aria/lora/utils.py:29-64): a module is a target when
+    its qualified name contains one of `lora_target_modules`, unless it lives in a frozen tower or a frozen LM layer."""
+    out = []
+    for key in model_named_modules:
+        if freeze_vit and "vision_tower" in key:
+            continue
+        if freeze_projector and "multi_modal_projector" in key:
+            continue
+        if freeze_llm and "language_model" in key:
+            continue
+        if any(f"language_model.model.layers.{i}." in key for i in (freeze_llm_layers or ())):
+            continue
+        if any(t in key for t in lora_target_modules):
+            out.append(key)
+    return out
+
+
+def inject_lora(model: nn.Module, target_modules, r: int = 8, lora_alpha: int = 32, adapter_name: str = "default") -> list:
+    """Wrap every `GroupedGEMM` whose qualified name is in `target_modules` (e.g. from `get_lora_target_modules`) with a
+    `GroupedGemmLoraLayer`, in place — the `{GroupedGEMM: GroupedGemmLoraLayer}` custom-module mapping of aria/train.py:107.
+    Returns the names wrapped.  Other module types in the list are left alone (their LoRA is peft's stock Linear path)."""
+    wanted, done = set(target_modules), []
+    for name, mod in list(model.named_modules()):
+        if name in wanted and type(mod) is GroupedGEMM:
+            parent = model.get_submodule(name.rsplit(".", 1)[0]) if "." in name else model
+            setattr(parent, name.rsplit(".", 1)[-1], GroupedGemmLoraLayer(mod, adapter_name, r=r, lora_alpha=lora_alpha))
+            done.append(name)
+    return done
+
+
 class GroupedGemmLoraLayer(nn.Module):
     """Same attribute names as the reference layer (`base_layer`, `lora_A`, `lora_B`, `scaling`, `r`, `lora_alpha`), one
     adapter per name; dropout is the identity (lora_dropout 0 in the recipe; a non-zero value is rejected)."""

@@ -180,8 +180,14 @@ class GroupedMLP(nn.Module):
 
     def forward(self, permuted_tokens, tokens_per_expert):
         off = _as_offsets(tokens_per_expert, self.fc1.groups, permuted_tokens.device)
-        h = ops.grouped_gemm(permuted_tokens, self.fc1.weight, off, swiglu=True)
-        return ops.grouped_gemm(h, self.fc2.weight, off)
+        if type(self.fc1) is GroupedGEMM and type(self.fc2) is GroupedGEMM:
+            h = ops.grouped_gemm(permuted_tokens, self.fc1.weight, off, swiglu=True)
+            return ops.grouped_gemm(h, self.fc2.weight, off)
+        # fc1 / fc2 wrapped by an adapter (aria_b200.lora.GroupedGemmLoraLayer, what peft does to the reference's
+        # GroupedGEMM modules, aria/train.py:107): call through the modules as the reference does (moe_lm.py:521-525);
+        # the glu runs as its own (differentiable) kernel because the adapter term must be added before it
+        from .lora import swiglu
+        return self.fc2(swiglu(self.fc1(permuted_tokens, off)), off)
 
 
 class SharedExpertMLP(nn.Module):

@@ -1,0 +1,109 @@
+"""GPU tests written after the round's GPU-minutes were spent: they exercise only kernels and wrappers that the verified
+tests already cover, in new combinations, but have NOT yet run on a B200.  They sit in the last-collected file and are
+non-strict xfail so that an unexpected failure here is reported (xfail / XPASS) without masking the verified suite under
+`pytest -x`.  Promote them into test_gpu_lora.py / test_gpu_ep.py once they have passed on hardware."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="not yet run on hardware (round-1 GPU budget exhausted)", strict=False)]
+DEV = "cuda"
+
+
+def _rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def test_grouped_gemm_lora_against_reference_golden():
+    """The bf16 fixture holds outputs and gradients of the UNMODIFIED reference layer (oracle/make_golden.py): compare the
+    CUDA path with it directly (no oracle in between)."""
+    import os
+    from aria_b200 import lora, moe_lm
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "lora_grouped_gemm_bf16.pt"), weights_only=False)
+    E, K, N = g["w"].shape
+    base = moe_lm.GroupedGEMM(K, N, E, device=DEV)
+    base.weight.data.copy_(g["w"].to(DEV))
+    layer = lora.GroupedGemmLoraLayer(base, "default", r=g["r"], lora_alpha=g["lora_alpha"])
+    layer.lora_A["default"].weight.data.copy_(g["a"].to(DEV))
+    layer.lora_B["default"].weight.data.copy_(g["b"].to(DEV))
+    xg = g["x"].to(DEV).requires_grad_(True)
+    with torch.enable_grad():
+        out = layer(xg, g["counts"])
+        out.backward(g["dy"].to(DEV))
+    assert _rel_l2(out.detach(), g["out"]) <= 1e-2
+    assert _rel_l2(layer.lora_A["default"].weight.grad, g["d_a"]) <= 2e-2
+    assert _rel_l2(layer.lora_B["default"].weight.grad, g["d_b"]) <= 2e-2
+    assert _rel_l2(xg.grad, g["dx"]) <= 2e-2
+    # merged weights: same function through the plain grouped GEMM
+    with torch.no_grad():
+        layer.merge()
+        merged = layer(g["x"].to(DEV), g["counts"])
+    assert _rel_l2(merged, g["out"]) <= 2e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices():
+    """The reference can span GPUs inside ONE process (`device_map="auto"`, aria/inference.py:55-57; hence the
+    `torch.cuda.set_device(input.device)` at moe_lm.py:483).  Every C-ABI call must honour the tensor's device: the
+    dynamic-shared-memory opt-ins and the SM count are per-device state inside the library."""
+    from aria_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 512, generator=g).bfloat16()
+    w = (torch.randn(384, 512, generator=g) * 0.05).bfloat16()
+    q = torch.randn(1, 2, 200, 128, generator=g).bfloat16()
+    ref = x.float() @ w.float().t()
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        y = ops.linear(x.to(dev), w.to(dev))
+        o = ops.attention(q.to(dev), q.to(dev), q.to(dev), 200, 200, 128 ** -0.5, True)
+        torch.cuda.synchronize(dev)
+        assert y.device == torch.device(dev)
+        assert float((y.float().cpu() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+        outs.append(o.float().cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+
+def test_grouped_mlp_with_lora_adapters_forward_backward_vs_oracle():
+    """`GroupedMLP` whose fc1 / fc2 were wrapped by `inject_lora` (what peft does to the reference, aria/train.py:107):
+    fc1+adapter -> glu -> fc2+adapter, forward and the four adapter gradients + dx against fp32 autograd through the oracle."""
+    from aria_b200 import lora, moe_lm
+    from oracle import aria_oracle as O
+    g = torch.Generator().manual_seed(21)
+    E, d, I, r, alpha = 4, 128, 128, 8, 32
+    cfg = moe_lm.AriaMoELMConfig(hidden_size=d, moe_num_experts=E, moe_topk=2, moe_intermediate_size=I)
+    mlp = moe_lm.GroupedMLP(cfg, device=DEV)
+    counts = torch.tensor([48, 16, 0, 64])
+    rows = int(counts.sum())
+    w1 = (torch.randn(E, d, 2 * I, generator=g) * 0.05).bfloat16()
+    w2 = (torch.randn(E, I, d, generator=g) * 0.05).bfloat16()
+    mlp.fc1.weight.data.copy_(w1.to(DEV))
+    mlp.fc2.weight.data.copy_(w2.to(DEV))
+    assert lora.inject_lora(mlp, ["fc1", "fc2"], r=r, lora_alpha=alpha) == ["fc1", "fc2"]
+    ab = {}
+    for name, K, N in (("fc1", d, 2 * I), ("fc2", I, d)):
+        a = (torch.randn(E, K, r, generator=g) * 0.05).bfloat16()
+        b = (torch.randn(E, r, N, generator=g) * 0.05).bfloat16()
+        layer = getattr(mlp, name)
+        layer.lora_A["default"].weight.data.copy_(a.to(DEV))
+        layer.lora_B["default"].weight.data.copy_(b.to(DEV))
+        ab[name] = (a.float().requires_grad_(True), b.float().requires_grad_(True))
+    x = torch.randn(rows, d, generator=g).bfloat16()
+    dy = torch.randn(rows, d, generator=g).bfloat16()
+    x32 = x.float().requires_grad_(True)
+    s = alpha / r
+    with torch.enable_grad():
+        h1 = O.grouped_gemm_lora(x32, w1.float(), *ab["fc1"], counts, s)
+        want = O.grouped_gemm_lora(O.glu(h1), w2.float(), *ab["fc2"], counts, s)
+        want.backward(dy.float())
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.enable_grad():
+        got = mlp(xg, counts)
+        got.backward(dy.to(DEV))
+    assert _rel_l2(got.detach(), want.detach()) <= 2e-2
+    assert _rel_l2(xg.grad, x32.grad) <= 3e-2
+    for name in ("fc1", "fc2"):
+        layer = getattr(mlp, name)
+        assert _rel_l2(layer.lora_A["default"].weight.grad, ab[name][0].grad) <= 3e-2, name
+        assert _rel_l2(layer.lora_B["default"].weight.grad, ab[name][1].grad) <= 3e-2, name
