@@ -58,8 +58,36 @@ class AriaForConditionalGeneration(nn.Module):
         self.vocab_size = t.vocab_size
         self.language_model = AriaMoELMForCausalLM(t, device)
 
+    # ---- modeling_aria.py:145-192: the helpers aria/train.py:70-75 and the recipes call on the model
+    def freeze_vit(self):
+        for p in self.vision_tower.parameters():
+            p.requires_grad = False
+
+    def freeze_projector(self):
+        for p in self.multi_modal_projector.parameters():
+            p.requires_grad = False
+
+    def freeze_llm(self):
+        for p in self.language_model.parameters():
+            p.requires_grad = False
+
     def get_input_embeddings(self):
-        return self.language_model.model.embed_tokens
+        return self.language_model.get_input_embeddings()
+
+    def set_input_embeddings(self, value):
+        self.language_model.set_input_embeddings(value)
+
+    def get_output_embeddings(self):
+        return self.language_model.get_output_embeddings()
+
+    def set_output_embeddings(self, value):
+        self.language_model.set_output_embeddings(value)
+
+    def set_moe_z_loss_coeff(self, value):
+        self.language_model.set_z_loss_coeff(value)
+
+    def set_moe_aux_loss_coeff(self, value):
+        self.language_model.set_aux_loss_coeff(value)
 
     def enable_expert_parallel(self, max_tokens: int, group=None):
         """Shard the routed experts of every MoE layer over the ranks of `group` (rank r serves experts

@@ -343,6 +343,25 @@ class AriaMoELMForCausalLM(nn.Module):
         c = self.config
         return KVCache(c.num_hidden_layers, B, c.num_attention_heads, T_max, c.head_dim, device)
 
+    # moe_lm.py:663-679: the routers read the coefficients from the shared config object (used by moe_train's router losses)
+    def set_z_loss_coeff(self, z_loss_coeff: float):
+        self.config.moe_z_loss_coeff = z_loss_coeff
+
+    def set_aux_loss_coeff(self, aux_loss_coeff: float):
+        self.config.moe_aux_loss_coeff = aux_loss_coeff
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, value):
+        self.lm_head = value
+
     def forward(self, inputs_embeds, cache: Optional[KVCache] = None, num_logits_to_keep: int = 0):
         B, T, _ = inputs_embeds.shape
         if cache is None:

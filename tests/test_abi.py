@@ -124,3 +124,27 @@ def test_bench_gpu_leg_does_not_touch_oracle():
     imports = re.findall(r"^\s*(?:from|import)\s+(\S+)", body, flags=re.M)
     assert not [m for m in imports if m.startswith("oracle")], imports
     assert "CpuReference" in body  # the one allowed use: the cpu_baseline leg at N=1
+
+
+def test_top_level_model_helpers_match_the_reference_api():
+    """modeling_aria.py:145-192 / moe_lm.py:663-679: freeze_*, embedding accessors, MoE loss-coefficient setters."""
+    from aria_b200 import configs as C
+    from aria_b200.modeling_aria import AriaConfig, AriaForConditionalGeneration
+    from oracle import configs as OC
+    model = AriaForConditionalGeneration(AriaConfig.from_dict(OC.TINY))
+    for p in model.parameters():
+        p.requires_grad = True
+    model.freeze_vit()
+    model.freeze_projector()
+    assert not any(p.requires_grad for p in model.vision_tower.parameters())
+    assert not any(p.requires_grad for p in model.multi_modal_projector.parameters())
+    assert all(p.requires_grad for p in model.language_model.parameters())
+    model.freeze_llm()
+    assert not any(p.requires_grad for p in model.parameters())
+    assert model.get_input_embeddings() is model.language_model.model.embed_tokens
+    assert model.get_output_embeddings() is model.language_model.lm_head
+    model.set_moe_z_loss_coeff(0.25)
+    model.set_moe_aux_loss_coeff(0.5)
+    router_cfg = model.language_model.model.layers[0].mlp.router.config
+    assert router_cfg.moe_z_loss_coeff == 0.25 and router_cfg.moe_aux_loss_coeff == 0.5
+    assert C.ARIA_25B["text_config"]["moe_num_experts"] == 64
