@@ -9,8 +9,8 @@ Seams:
   4. `Idefics2EncoderLayer.forward` (vision_encoder.py:120) -> fused ViT layer
 
 (1) and (2) are wired by `install()`; (3) is `aria_b200.hf_attention.register()` (an implementation key for transformers'
-attention interface — the module keeps its projections, RoPE and HF Cache); (4) needs the mask plumbing of the host
-transformers version and is exposed as the standalone mirror in `aria_b200.vision_encoder` (load the same state dict).
+attention interface — the module keeps its projections, RoPE and HF Cache); (4) is `install_vit()` (per-layer forward on the
+HF module's own parameters; the embeddings / mask creation around it stay HF's).
 There is no CPU fallback: the patched modules require CUDA bf16 tensors.
 """
 from __future__ import annotations
@@ -36,6 +36,54 @@ def _moe_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
     se = self.shared_experts
     shared = ops.linear(ops.linear_swiglu(x, se.gate_proj.weight, se.up_proj.weight), se.down_proj.weight)
     return ops.unpermute_combine(y, dest, scores, shared).view(shape)
+
+
+def _vit_layer_forward(self, hidden_states: torch.Tensor, attention_mask=None, *args, **kwargs):
+    """Replacement for transformers' `Idefics2EncoderLayer.forward` (what `AriaVisionTransformer` is built from,
+    vision_encoder.py:65-67,120), on the module's own parameters: LN -> fused q/k/v GEMM with head scatter -> non-causal attention
+    (hd 72 carried in 128-wide rows, key mask) -> out_proj (+residual) -> LN -> fc1 (+bias, gelu_tanh) -> fc2 (+bias, +residual).
+    `attention_mask`: None, the 4-D additive mask [B,1,N,N] HF builds from the patch mask, or a 2-D validity mask [B,N]."""
+    from . import _lib as L
+    a, m = self.self_attn, self.mlp
+    B, N, _ = hidden_states.shape
+    H, hd = a.num_heads, a.head_dim
+    key_mask = None
+    if attention_mask is not None:
+        if attention_mask.dim() == 4:
+            key_mask = (attention_mask[:, 0, 0, :] < 0).to(torch.uint8).contiguous()
+        else:
+            key_mask = (~attention_mask.bool()).to(torch.uint8).contiguous()
+    buf = getattr(self, "_aria_qkv", None)
+    if buf is None or buf[0].shape != (B, H, N, 128) or buf[0].device != hidden_states.device:
+        buf = [torch.zeros(B, H, N, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3)]
+        self._aria_qkv = buf            # pad columns hd..127 stay zero across calls
+    x = hidden_states.contiguous()
+    h = ops.layernorm(x, self.layer_norm1.weight, self.layer_norm1.bias, self.layer_norm1.eps)
+    ops.qkv_heads(h, [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias],
+                  buf, hd, N)
+    o = ops.attention(buf[0], buf[1], buf[2], N, N, hd ** -0.5, causal=False, out_hd=hd, key_mask=key_mask)
+    x = ops.linear(o, a.out_proj.weight, a.out_proj.bias, residual=x)
+    h = ops.layernorm(x, self.layer_norm2.weight, self.layer_norm2.bias, self.layer_norm2.eps)
+    h = ops.linear(h, m.fc1.weight, m.fc1.bias, act=L.ACT_GELU_TANH)
+    out = ops.linear(h, m.fc2.weight, m.fc2.bias, residual=x)
+    return (out,) if getattr(self, "_aria_returns_tuple", False) else out
+
+
+def install_vit(model) -> int:
+    """Seam 3: patch every `Idefics2EncoderLayer` inside `model` (the reference's vision tower) with `_vit_layer_forward`.
+    transformers 4.46 layers return a 1-tuple, 5.x layers the tensor: detected from the original signature.  Returns the number
+    of layers patched.  Requires `hidden_act = gelu_pytorch_tanh` (what Aria uses); anything else is rejected."""
+    import inspect
+    n = 0
+    for mod in model.modules():
+        if type(mod).__name__ == "Idefics2EncoderLayer" and hasattr(mod, "self_attn") and hasattr(mod, "layer_norm1"):
+            act = type(getattr(mod.mlp, "activation_fn", None)).__name__
+            if act not in ("GELUTanh", "PytorchGELUTanh"):
+                raise NotImplementedError(f"install_vit: unsupported MLP activation {act} (the fused epilogue is gelu_pytorch_tanh)")
+            mod._aria_returns_tuple = "output_attentions" in inspect.signature(type(mod).forward).parameters
+            mod.forward = types.MethodType(_vit_layer_forward, mod)
+            n += 1
+    return n
 
 
 def install(model, reference_moe_lm_module=None) -> int:

@@ -154,3 +154,19 @@ def test_grouped_gemm_lora_layer_live(dtype):
             merged = layer(x0, counts)
         assert (merged - want.detach()).abs().max() <= 1e-5
         assert (base.weight - (w + torch.matmul(a, b) * (alpha / r))).abs().max() <= 1e-7
+
+
+def test_install_vit_rebinds_the_reference_vision_layers():
+    """Seam 3 wiring (executing the patched layers needs CUDA): every Idefics2EncoderLayer of the reference vision tower is
+    patched, the tuple/tensor return convention of the host transformers version is detected, and CPU input fails loudly."""
+    from aria_b200 import install
+    ref = load_reference()
+    vc = ref.vision_encoder.AriaVisionConfig(hidden_size=144, num_attention_heads=2, num_hidden_layers=2, intermediate_size=256,
+                                             patch_size=14, image_size=56, hidden_act="gelu_pytorch_tanh")
+    vc._attn_implementation = "eager"
+    tower = ref.vision_encoder.AriaVisionModel(vc)
+    assert install.install_vit(tower) == 2
+    layer = tower.vision_model.encoder.layers[0]
+    assert layer.forward.__func__ is install._vit_layer_forward and layer._aria_returns_tuple is False   # transformers 5.x here
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(1, 16, 144, dtype=torch.bfloat16), None)
