@@ -1,7 +1,14 @@
-"""GPU tests written after the round's GPU-minutes were spent: they exercise only kernels and wrappers that the verified
-tests already cover, in new combinations, but have NOT yet run on a B200.  They sit in the last-collected file and are
-non-strict xfail so that an unexpected failure here is reported (xfail / XPASS) without masking the verified suite under
-`pytest -x`.  Promote them into test_gpu_lora.py / test_gpu_ep.py once they have passed on hardware."""
+"""GPU tests written after the round's GPU-minutes were almost spent.  They sit in the last-collected file and are non-strict
+xfail so that a failure here is reported (xfail / XPASS) without masking the verified suite under `pytest -x`.
+
+State after the one 13-second run the remaining budget allowed (round 1, B200):
+  * test_grouped_gemm_lora_against_reference_golden (E=4, in=128, out=192, 128 rows)            FAILED  - cause not yet identified
+  * test_grouped_mlp_with_lora_adapters_forward_backward_vs_oracle (E=4, d=I=128, 128 rows)    FAILED  - cause not yet identified
+    (the LoRA layer itself passes on hardware at E=8, in=256, out=384, 416 rows: tests/test_gpu_lora.py; the failures left no
+     sticky CUDA error - the tests after them passed - so they are assertion mismatches or argument checks, to be debugged
+     first thing in round 2: `pytest tests/test_zz_gpu_round1_unverified.py -q --runxfail`)
+  * test_one_process_two_devices                                                                 not run (needs 2 GPUs)
+The two `install_vit` tests that were here passed (XPASS) and moved to tests/test_install_vit.py."""
 import pytest
 import torch
 
@@ -108,38 +115,3 @@ def test_grouped_mlp_with_lora_adapters_forward_backward_vs_oracle():
         assert _rel_l2(layer.lora_A["default"].weight.grad, ab[name][0].grad) <= 3e-2, name
         assert _rel_l2(layer.lora_B["default"].weight.grad, ab[name][1].grad) <= 3e-2, name
 
-
-@pytest.mark.parametrize("padded", [False, True])
-def test_install_vit_layer_matches_hf_eager(padded):
-    """Seam 3: transformers' own Idefics2EncoderLayer (what the reference vision tower is built from) patched by
-    `install_vit` vs the same layer run by HF in fp32 eager mode; hd = 72, optional key padding as a 4-D additive mask."""
-    import copy
-    from transformers.models.idefics2.modeling_idefics2 import Idefics2EncoderLayer, Idefics2VisionConfig
-    from aria_b200 import install
-    torch.manual_seed(5)
-    cfg = Idefics2VisionConfig(hidden_size=144, num_attention_heads=2, intermediate_size=256, num_hidden_layers=1,
-                               hidden_act="gelu_pytorch_tanh")
-    cfg._attn_implementation = "eager"
-    ref_layer = Idefics2EncoderLayer(cfg).float().cuda().eval()
-    for p_ in ref_layer.parameters():                       # bf16-representable weights so both sides see the same values
-        p_.data = (torch.randn_like(p_) * 0.05).bfloat16().float()
-    ref_layer.layer_norm1.weight.data += 1.0
-    ref_layer.layer_norm2.weight.data += 1.0
-    ours = copy.deepcopy(ref_layer).bfloat16()
-    holder = torch.nn.ModuleList([ours])
-    assert install.install_vit(holder) == 1
-    B, N = 2, 200
-    x = torch.randn(B, N, 144, device="cuda").bfloat16()
-    mask = None
-    if padded:
-        valid = torch.ones(B, N, dtype=torch.bool, device="cuda")
-        valid[0, 150:] = False
-        mask = torch.zeros(B, 1, N, N, device="cuda").masked_fill(~valid[:, None, None, :], torch.finfo(torch.float32).min)
-    with torch.no_grad():
-        want = ref_layer(x.float(), mask)
-        got = ours(x, mask)
-    want = want[0] if isinstance(want, tuple) else want
-    got = got[0] if isinstance(got, tuple) else got
-    rows = slice(None) if not padded else (slice(None), slice(0, 150))   # padded query rows are don't-care downstream
-    err = (got.float()[rows] - want[rows]).abs().max() / want[rows].abs().max()
-    assert float(err) <= 2e-2, float(err)
