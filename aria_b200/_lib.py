@@ -50,6 +50,7 @@ SIGNATURES = {
     "aria_offsets_from_counts": (i32, [vp, vp, i32, vp]),
     "aria_router_topk": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "aria_route_from_logits": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
+    "aria_route_given_indices": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_build_permutation": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "aria_grouped_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i64, i64, i64, i32, i32, vp]),
     "aria_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
@@ -77,7 +78,7 @@ SIGNATURES = {
     "aria_ep_layout": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
     "aria_scatter_rows_grouped": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, i64, vp]),
     "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),
-    "aria_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i64, vp]),
+    "aria_attention_decode": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i64, vp]),
     "aria_attention_decode_workspace_bytes": (i64, [i32, i32, i32]),
 }
 

@@ -328,7 +328,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 constexpr int DEC_SPLIT_KEYS = 256;
 
 __global__ void __launch_bounds__(128) attn_decode_partial(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                                                           const __nv_bfloat16* __restrict__ vc, float* __restrict__ ws, int H, int Tk,
+                                                           const __nv_bfloat16* __restrict__ vc, const uint8_t* __restrict__ key_mask,
+                                                           float* __restrict__ ws, int H, int Tk,
                                                            int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b,
                                                            int64_t kv_stride_h, float scale_log2, int splits) {
   const int bh = blockIdx.x, split = blockIdx.y;
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(128) attn_decode_partial(const __nv_bfloat16* 
   const int k_begin = split * DEC_SPLIT_KEYS, k_end = min(Tk, k_begin + DEC_SPLIT_KEYS);
   const __nv_bfloat16* kbase = kc + b * kv_stride_b + h * kv_stride_h;
   const __nv_bfloat16* vbase = vc + b * kv_stride_b + h * kv_stride_h;
+  const uint8_t* km = key_mask ? key_mask + static_cast<int64_t>(b) * Tk : nullptr;
   const uint2 qv = *reinterpret_cast<const uint2*>(q + b * q_stride_b + h * q_stride_h + lane * 4);
   const float q0 = bf16_lo(qv.x) * scale_log2, q1 = bf16_hi(qv.x) * scale_log2, q2 = bf16_lo(qv.y) * scale_log2,
               q3 = bf16_hi(qv.y) * scale_log2;
@@ -344,10 +346,12 @@ __global__ void __launch_bounds__(128) attn_decode_partial(const __nv_bfloat16* 
   for (int k0 = k_begin + warp * 4; k0 < k_end; k0 += 16) {
     float s[4];
     uint2 vv[4];
+    bool live[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int kk = k0 + u;
-      if (kk < k_end) {
+      live[u] = kk < k_end && !(km && km[kk]);
+      if (live[u]) {
         const uint2 kv = __ldg(reinterpret_cast<const uint2*>(kbase + static_cast<int64_t>(kk) * AT_D + lane * 4));
         vv[u] = __ldg(reinterpret_cast<const uint2*>(vbase + static_cast<int64_t>(kk) * AT_D + lane * 4));
         s[u] = q0 * bf16_lo(kv.x) + q1 * bf16_hi(kv.x) + q2 * bf16_lo(kv.y) + q3 * bf16_hi(kv.y);
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(128) attn_decode_partial(const __nv_bfloat16* 
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (k0 + u < k_end) {
+      if (live[u]) {
         const float m_new = fmaxf(m, s[u]);
         const float f = exp2f(m - m_new), pw = exp2f(s[u] - m_new);
         l = l * f + pw;
@@ -470,7 +474,7 @@ extern "C" int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, i
   return static_cast<int64_t>(B) * H * splits * (AT_D + 2) * sizeof(float);
 }
 
-extern "C" int aria_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tk,
+extern "C" int aria_attention_decode(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask, int32_t B, int32_t H, int32_t Tk,
                                      int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b, int64_t kv_stride_h,
                                      float scale, void* workspace, int64_t workspace_bytes, aria_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -479,7 +483,7 @@ extern "C" int aria_attention_decode(const void* q, const void* k, const void* v
   const int splits = (Tk + DEC_SPLIT_KEYS - 1) / DEC_SPLIT_KEYS;
   dim3 grid(B * H, splits);
   attn_decode_partial<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
-                                                static_cast<const __nv_bfloat16*>(v), static_cast<float*>(workspace), H, Tk,
+                                                static_cast<const __nv_bfloat16*>(v), key_mask, static_cast<float*>(workspace), H, Tk,
                                                 q_stride_b, q_stride_h, kv_stride_b, kv_stride_h, scale * 1.4426950408889634f, splits);
   int rc = check_launch("attn_decode_partial");
   if (rc) return rc;

@@ -61,9 +61,25 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const uint
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  // cuTensorMapEncodeTiled is a DRIVER entry point: it needs a CUDA context bound to the calling thread.  The runtime binds
+  // the primary context lazily, on a thread's first runtime call that needs it — and a fresh thread whose current device is
+  // already the wanted one (PyTorch's autograd worker: its device guard skips cudaSetDevice when cudaGetDevice() matches)
+  // has none.  The first C-ABI call of such a thread then failed with CUDA_ERROR_INVALID_CONTEXT (201): the round-1
+  // "nondeterministic LoRA test" (a backward whose first node is one of our GEMMs).  cudaFree(0) binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {  // e.g. the context was popped by another library
+    cudaFree(0);
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "aria_b200: cuTensorMapEncodeTiled failed (%d): rank %d ptr %p dims %llu,%llu stride %llu box %u,%u\n",
             (int)r, rank, ptr, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

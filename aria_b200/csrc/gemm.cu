@@ -441,5 +441,5 @@ extern "C" int aria_grouped_gemm(const void* a, const void* b, void* out, const 
   return aria_gemm(&d, stream);
 }
 
-extern "C" int aria_abi_version(void) { return 1; }
+extern "C" int aria_abi_version(void) { return 2; }
 extern "C" const char* aria_build_arch(void) { return "sm_100a"; }

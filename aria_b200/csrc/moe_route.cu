@@ -76,6 +76,37 @@ __global__ void __launch_bounds__(256) route_kernel(const __nv_bfloat16* __restr
     if (hist[i]) atomicAdd(&counts[i], hist[i]);
 }
 
+// Routing with the expert choice GIVEN (parity / replay hook, TopKRouter.forced_top_indices): scores = fp32 softmax over the
+// k logits at the given ids in the given order (moe_lm.py:262), counts = histogram (:264-269).  One warp per token.
+__global__ void __launch_bounds__(256) route_given_kernel(const __nv_bfloat16* __restrict__ logits, const int32_t* __restrict__ top_idx,
+                                                          __nv_bfloat16* __restrict__ scores, int32_t* __restrict__ counts,
+                                                          int64_t T, int E, int k) {
+  __shared__ int hist[MAX_E];
+  for (int i = threadIdx.x; i < MAX_E; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * warps_per_block;
+  for (int64_t t = warp_global; t < T; t += warp_stride) {
+    const int id = lane < k ? top_idx[t * k + lane] : 0;
+    const float v = lane < k ? __bfloat162float(logits[t * E + id]) : -INFINITY;
+    float vmax = v;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+    const float e = lane < k ? expf(v - vmax) : 0.f;
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s += __shfl_sync(0xffffffffu, e, j);
+    if (lane < k) {
+      scores[t * k + lane] = __float2bfloat16_rn(e / s);
+      atomicAdd(&hist[id], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
 // Stable counting sort, one block per expert: dest_row[i] = offsets[e] + #{i' < i : id[i'] == e}.
 __global__ void __launch_bounds__(1024) permutation_kernel(const int32_t* __restrict__ top_idx,
                                                            const int32_t* __restrict__ counts,
@@ -229,6 +260,18 @@ extern "C" int aria_route_from_logits(const void* logits, int32_t* top_idx, void
   route_kernel<<<grid_for_warps(T, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), top_idx,
                                                          static_cast<__nv_bfloat16*>(scores), counts, T, E, k);
   return check_launch("route_kernel");
+}
+
+extern "C" int aria_route_given_indices(const void* logits, const int32_t* top_idx, void* scores, int32_t* counts, int64_t T,
+                                        int32_t E, int32_t k, aria_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ARIA_CHECK_ARG(logits && top_idx && scores && counts);
+  ARIA_CHECK_ARG(E >= 1 && E <= MAX_E && k >= 1 && k <= MAX_K && k <= E && T >= 0);
+  if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * E, stream) != cudaSuccess) return ARIA_ERR_CUDA;
+  if (T == 0) return ARIA_OK;
+  route_given_kernel<<<grid_for_warps(T, 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), top_idx,
+                                                               static_cast<__nv_bfloat16*>(scores), counts, T, E, k);
+  return check_launch("route_given_kernel");
 }
 
 extern "C" int aria_router_topk(const void* x, const void* w_router, void* logits_out, int32_t* top_idx, void* scores,

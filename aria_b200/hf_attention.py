@@ -10,7 +10,8 @@ for a purely causal batch and the 2-D padding mask otherwise).  The module keeps
     prefill / chunked prefill (Tq > 1)  -> aria_attention_fwd   (causal, queries are the last Tq positions of Tk keys)
     decode (Tq == 1)                    -> aria_attention_decode (split-KV streaming kernel)
 
-No fallback: MHA with head_dim 128, bf16, CUDA, no dropout, no padding mask — anything else raises.
+Padded batches: the 2-D padding mask becomes the kernels' key mask (prefill and decode).
+No fallback: MHA with head_dim 128, bf16, CUDA, no dropout, no autograd — anything else raises.
 (Our own mirror `aria_b200.moe_lm.AriaAttention` fuses q/k/v + RoPE + the cache write into the projection GEMM and is what
 bench.py times; this seam exists so that an unmodified HF/reference model can switch the core by changing one config string.)
 """
@@ -32,9 +33,8 @@ def aria_b200_attention_forward(module, query: torch.Tensor, key: torch.Tensor, 
     (attn_output [B, Tq, H, 128], None) — the contract of transformers' attention interface."""
     if dropout:
         raise NotImplementedError("aria_b200 attention: dropout is not supported (inference / frozen-attention path)")
-    if attention_mask is not None:
-        raise NotImplementedError("aria_b200 attention: padded batches are not supported on this seam "
-                                  "(the FA2-style mask factory passes None for a fully causal batch)")
+    if torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad):
+        raise RuntimeError("aria_b200 attention: inference-only core (no autograd through the kernel); run under torch.no_grad()")
     if is_causal is False or getattr(module, "is_causal", True) is False:
         raise NotImplementedError("aria_b200 attention: only causal self-attention goes through this seam")
     B, H, Tq, hd = query.shape
@@ -43,15 +43,26 @@ def aria_b200_attention_forward(module, query: torch.Tensor, key: torch.Tensor, 
     if hd != 128:
         raise NotImplementedError(f"aria_b200 attention: head_dim must be 128, got {hd}")
     Tk = key.shape[2]
+    key_mask = None
+    if attention_mask is not None:
+        # padded batch: the FA2-style mask factory hands over the 2-D padding mask [B, Tk] (1 = real token); a 4-D additive
+        # or boolean mask (other factories) is accepted when it is "causal + key padding", which is all a causal LM produces
+        m = attention_mask
+        if m.dim() == 4:
+            last = m[:, 0, -1, :]                      # the last query row sees every non-padded key
+            m = last if last.dtype == torch.bool else (last >= 0)
+        if m.dim() != 2 or m.shape[0] != B or m.shape[1] < Tk:
+            raise NotImplementedError(f"aria_b200 attention: unsupported attention_mask shape {tuple(attention_mask.shape)}")
+        key_mask = (m[:, -Tk:] == 0).to(torch.uint8).contiguous()
     scale = float(scaling) if scaling is not None else hd ** -0.5
     k = key.contiguous()
     v = value.contiguous()
     if k.stride() != v.stride():
         v = v.clone(memory_format=torch.contiguous_format)
     if Tq == 1:
-        out = ops.attention_decode(query.reshape(B, H, hd).contiguous(), k, v, Tk, scale)       # [B, H*128]
+        out = ops.attention_decode(query.reshape(B, H, hd).contiguous(), k, v, Tk, scale, key_mask=key_mask)   # [B, H*128]
         return out.view(B, 1, H, hd), None
-    out = ops.attention(query.contiguous(), k, v, Tq, Tk, scale, True)                           # [B, Tq, H*128]
+    out = ops.attention(query.contiguous(), k, v, Tq, Tk, scale, True, key_mask=key_mask)        # [B, Tq, H*128]
     return out.view(B, Tq, H, hd), None
 
 

@@ -23,11 +23,22 @@ from . import moe_lm as _m
 from . import ops
 
 
+def _reject_autograd(what: str, module, *tensors):
+    """The seams below are the INFERENCE path: their outputs come straight from the C ABI and carry no grad_fn, so under
+    autograd they would silently cut the graph (and drop the training-mode router losses, moe_lm.py:257-272).  Refuse
+    instead of training with wrong gradients; fine-tuning goes through aria_b200.moe_train / aria_b200.lora."""
+    if torch.is_grad_enabled() and (module.training or any(t is not None and t.requires_grad for t in tensors)):
+        raise RuntimeError(f"aria_b200.install: {what} is inference-only (no autograd through the fused kernels); call it under "
+                           "torch.no_grad() with the module in eval() mode, or use aria_b200.moe_train / aria_b200.lora to train")
+
+
 def _moe_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
-    """Replacement for the reference `MoELayer.forward` using the reference module's own parameters."""
-    cfg = self.router.config
+    """Replacement for the reference `MoELayer.forward` (moe_lm.py:548-577) — and for transformers' own `AriaTextMoELayer.forward`,
+    which has the same sub-modules with `router` an nn.Linear — using the module's own parameters."""
+    _reject_autograd("MoELayer.forward", self, hidden_states)
+    cfg = getattr(self.router, "config", None) or self.config
     shape = hidden_states.shape
-    x = hidden_states.reshape(-1, shape[-1])
+    x = hidden_states.reshape(-1, shape[-1]).contiguous()
     scores, idx, counts, _ = ops.router_topk(x, self.router.weight, cfg.moe_topk)
     offsets, dest, src = ops.build_permutation(idx, counts)
     permuted = ops.permute_rows(x, src)
@@ -44,12 +55,15 @@ def _vit_layer_forward(self, hidden_states: torch.Tensor, attention_mask=None, *
     (hd 72 carried in 128-wide rows, key mask) -> out_proj (+residual) -> LN -> fc1 (+bias, gelu_tanh) -> fc2 (+bias, +residual).
     `attention_mask`: None, the 4-D additive mask [B,1,N,N] HF builds from the patch mask, or a 2-D validity mask [B,N]."""
     from . import _lib as L
+    _reject_autograd("Idefics2EncoderLayer.forward", self, hidden_states)
     a, m = self.self_attn, self.mlp
     B, N, _ = hidden_states.shape
     H, hd = a.num_heads, a.head_dim
     key_mask = None
     if attention_mask is not None:
-        if attention_mask.dim() == 4:
+        if attention_mask.dim() == 4 and attention_mask.dtype == torch.bool:      # sdpa-style mask: True = may attend
+            key_mask = (~attention_mask[:, 0, 0, :]).to(torch.uint8).contiguous()
+        elif attention_mask.dim() == 4:
             key_mask = (attention_mask[:, 0, 0, :] < 0).to(torch.uint8).contiguous()
         else:
             key_mask = (~attention_mask.bool()).to(torch.uint8).contiguous()
@@ -76,7 +90,9 @@ def install_vit(model) -> int:
     import inspect
     n = 0
     for mod in model.modules():
-        if type(mod).__name__ == "Idefics2EncoderLayer" and hasattr(mod, "self_attn") and hasattr(mod, "layer_norm1"):
+        # Idefics2EncoderLayer: the reference's tower (vision_encoder.py:26-28,65-67); Idefics3EncoderLayer: the identical layer
+        # transformers' own `models.aria` builds its tower from
+        if type(mod).__name__ in ("Idefics2EncoderLayer", "Idefics3EncoderLayer") and hasattr(mod, "self_attn") and hasattr(mod, "layer_norm1"):
             act = type(getattr(mod.mlp, "activation_fn", None)).__name__
             if act not in ("GELUTanh", "PytorchGELUTanh"):
                 raise NotImplementedError(f"install_vit: unsupported MLP activation {act} (the fused epilogue is gelu_pytorch_tanh)")
@@ -91,7 +107,8 @@ def install(model, reference_moe_lm_module=None) -> int:
     Returns the number of layers patched.  Idempotent."""
     n = 0
     for mod in model.modules():
-        if type(mod).__name__ == "MoELayer" and hasattr(mod, "router") and hasattr(mod, "experts") and hasattr(mod, "shared_experts"):
+        if type(mod).__name__ in ("MoELayer", "AriaTextMoELayer") and hasattr(mod, "router") and hasattr(mod, "experts") \
+                and hasattr(mod, "shared_experts"):
             mod.forward = types.MethodType(_moe_forward, mod)
             n += 1
     if reference_moe_lm_module is not None:

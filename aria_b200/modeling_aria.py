@@ -1,9 +1,11 @@
 """Host-side mirror of `aria/model/modeling_aria.py`: AriaForConditionalGeneration.forward()/generate() with the
 Hugging Face state-dict layout, running entirely on the B200-native kernels.
 
-forward() follows modeling_aria.py:194-335: embed -> vision tower -> projector -> masked_scatter merge -> LM.
-Differences that are deliberate: no autograd / labels path (inference hot path only), the KV cache is our
-static `KVCache` (HF layout [B,H,T,hd] per layer), integer index tensors stay int32 on the device.
+forward() follows modeling_aria.py:194-335: embed -> vision tower -> projector -> masked_scatter merge -> LM, with the
+reference's argument list (attention_mask, position_ids, labels -> loss, ...).  Differences that are deliberate: no
+autograd through this class (inference hot path; training = moe_train / lora), the KV cache is our static `KVCache`
+(HF layout [B,H,T,hd] per layer), integer index tensors stay int32 on the device.  The drop-in surface for an
+*unmodified* HF / reference model is aria_b200.install + aria_b200.hf_attention (tests/test_gpu_dropin.py).
 """
 from __future__ import annotations
 
@@ -116,14 +118,32 @@ class AriaForConditionalGeneration(nn.Module):
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor = None, pixel_values: Optional[torch.Tensor] = None,
-                pixel_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
-                inputs_embeds: Optional[torch.Tensor] = None, num_logits_to_keep: int = 0,
-                max_cache_len: Optional[int] = None, input_ids_host: Optional[torch.Tensor] = None,
-                **_unused) -> AriaCausalLMOutputWithPast:
-        """input_ids / pixel_values / pixel_mask may be HOST tensors (pinned for async copies): they are copied to
+                pixel_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
+                inputs_embeds: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                use_cache: Optional[bool] = None, output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None,
+                cache_position: Optional[torch.Tensor] = None, num_logits_to_keep: int = 0,
+                max_cache_len: Optional[int] = None, input_ids_host: Optional[torch.Tensor] = None) -> AriaCausalLMOutputWithPast:
+        """Same arguments as the reference forward (modeling_aria.py:194-210); `max_cache_len` / `input_ids_host` are ours.
+
+        input_ids / pixel_values / pixel_mask may be HOST tensors (pinned for async copies): they are copied to
         the device on the current stream; image-token bookkeeping is then done on the host copy (no device sync).
         Device-resident input_ids cost one sync for the image-token count check, like the reference's `.item()`
-        (modeling_aria.py:265)."""
+        (modeling_aria.py:265).
+
+        attention_mask: the HF 2-D padding mask [B, past + T] (1 = real token).  Padded keys are masked inside the attention
+        kernels (prefill and decode).  position_ids [B, T]: RoPE positions (default: cache positions, as in LlamaModel).
+        labels: shifted cross-entropy exactly as modeling_aria.py:300-323 (the loss itself is torch glue on our logits;
+        this class is the inference path, so it carries no grad_fn — training goes through aria_b200.moe_train / lora).
+        Not supported, and rejected loudly: output_attentions / output_hidden_states (no such tensors exist in the fused
+        path), return_dict=False."""
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("aria_b200: attention weights / per-layer hidden states are not materialised by the fused path")
+        if return_dict is False:
+            raise NotImplementedError("aria_b200: tuple outputs are not supported (return_dict=False)")
+        if cache_position is not None and past_key_values is not None and int(cache_position.reshape(-1)[0]) != past_key_values.seq_len:
+            raise NotImplementedError("aria_b200: cache_position must continue the KV cache (static cache, append-only)")
         dev = self.device
         ids_host = input_ids_host  # optional host copy of device-resident ids (bookkeeping without a sync)
         if input_ids is not None and not input_ids.is_cuda:
@@ -133,6 +153,8 @@ class AriaForConditionalGeneration(nn.Module):
             pixel_values = pixel_values.to(dev, non_blocking=True)
         if inputs_embeds is None:
             inputs_embeds = ops.embedding(input_ids.contiguous(), self.get_input_embeddings().weight)
+        elif pixel_values is not None:
+            inputs_embeds = inputs_embeds.clone()   # the merge below writes in place; the reference's masked_scatter does not
 
         if pixel_values is not None:
             feats, image_attn_mask = self.vision_tower(pixel_values.to(bf16), pixel_mask)
@@ -151,19 +173,77 @@ class AriaForConditionalGeneration(nn.Module):
         cache = past_key_values
         if cache is None:
             cache = self.language_model.new_cache(B, max_cache_len or T, dev)
-        logits, cache = self.language_model(inputs_embeds, cache, num_logits_to_keep)
-        return AriaCausalLMOutputWithPast(logits, cache)
+        key_mask = None
+        if attention_mask is not None:
+            if attention_mask.shape != (B, cache.seq_len + T):
+                raise ValueError(f"attention_mask must be [B, past + T] = {(B, cache.seq_len + T)}, got {tuple(attention_mask.shape)}")
+            if not bool((attention_mask != 0).all()):      # host tensor: free; device tensor: one sync, only when a mask is given
+                key_mask = (attention_mask == 0).to(device=dev, dtype=torch.uint8).contiguous()
+        pos = None
+        if position_ids is not None:
+            if position_ids.shape != (B, T):
+                raise ValueError(f"position_ids must be [B, T] = {(B, T)}, got {tuple(position_ids.shape)}")
+            pos = position_ids.to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
+        logits, cache = self.language_model(inputs_embeds, cache, num_logits_to_keep, key_mask=key_mask, position_ids=pos)
+        out = AriaCausalLMOutputWithPast(logits, cache)
+        if labels is not None:
+            out.loss = self._shifted_cross_entropy(logits, labels, attention_mask)
+        return out
+
+    @staticmethod
+    def _shifted_cross_entropy(logits, labels, attention_mask):
+        """modeling_aria.py:300-323, verbatim semantics: tokens < n predict n; padded positions dropped through the 2-D mask."""
+        labels = labels.to(logits.device)
+        if attention_mask is not None:
+            shift_mask = attention_mask[:, -(logits.shape[1] - 1):].to(logits.device)
+            shift_logits = logits[..., :-1, :][shift_mask != 0].contiguous()
+            shift_labels = labels[..., 1:][shift_mask != 0].contiguous()
+        else:
+            shift_logits = logits[..., :-1, :].contiguous()
+            shift_labels = labels[..., 1:].contiguous()
+        return nn.functional.cross_entropy(shift_logits.view(-1, shift_logits.size(-1)).float(), shift_labels.view(-1))
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, pixel_values=None,
+                                      pixel_mask=None, attention_mask=None, cache_position=None, num_logits_to_keep=None,
+                                      **kwargs):
+        """modeling_aria.py:337-365: with a non-empty cache only the new token ids go in; pixel inputs only at step 0;
+        position ids from the padding mask (what LlamaForCausalLM.prepare_inputs_for_generation derives)."""
+        past = 0 if past_key_values is None else past_key_values.seq_len
+        model_inputs = {"input_ids": input_ids[:, past:] if past else input_ids, "past_key_values": past_key_values,
+                        "attention_mask": attention_mask}
+        if inputs_embeds is not None and not past:
+            model_inputs = {"inputs_embeds": inputs_embeds, "input_ids": input_ids, "past_key_values": past_key_values,
+                            "attention_mask": attention_mask}
+        if attention_mask is not None:
+            pos = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)
+            model_inputs["position_ids"] = pos[:, past:] if past else pos
+        if num_logits_to_keep is not None:
+            model_inputs["num_logits_to_keep"] = num_logits_to_keep
+        if not past:
+            model_inputs["pixel_values"] = pixel_values
+            model_inputs["pixel_mask"] = pixel_mask
+        return model_inputs
 
     @torch.no_grad()
-    def generate(self, input_ids, pixel_values=None, pixel_mask=None, max_new_tokens: int = 16):
+    def generate(self, input_ids, pixel_values=None, pixel_mask=None, max_new_tokens: int = 16, attention_mask=None):
         """Greedy decoding (the reference goes through HF GenerationMixin, modeling_aria.py:125,337-365):
-        prefill with the image, then one token per step against the KV cache (pixel inputs only at step 0)."""
+        prefill with the image, then one token per step against the KV cache (pixel inputs only at step 0).
+        attention_mask [B, T]: LEFT-padded batches of ragged prompts (the HF generation convention); positions are derived
+        from it as GenerationMixin does."""
         B, T = input_ids.shape
-        out = self.forward(input_ids, pixel_values, pixel_mask, num_logits_to_keep=1, max_cache_len=T + max_new_tokens)
+        mask = None if attention_mask is None else attention_mask.to("cpu", torch.long)
+        inputs = self.prepare_inputs_for_generation(input_ids, None, pixel_values=pixel_values, pixel_mask=pixel_mask,
+                                                    attention_mask=mask, num_logits_to_keep=1)
+        out = self.forward(**inputs, max_cache_len=T + max_new_tokens)
         cache = out.past_key_values
         tokens = [out.logits[:, -1].float().argmax(-1)]
+        all_ids = input_ids.to(tokens[0].device)
         for _ in range(max_new_tokens - 1):
-            step = self.forward(tokens[-1].view(B, 1), past_key_values=cache, num_logits_to_keep=1)
+            all_ids = torch.cat([all_ids, tokens[-1].view(B, 1)], dim=1)
+            if mask is not None:
+                mask = torch.cat([mask, torch.ones(B, 1, dtype=torch.long)], dim=1)
+            inputs = self.prepare_inputs_for_generation(all_ids, cache, attention_mask=mask, num_logits_to_keep=1)
+            step = self.forward(**inputs)
             tokens.append(step.logits[:, -1].float().argmax(-1))
         return torch.cat([input_ids.to(tokens[0].device), torch.stack(tokens, 1)], dim=1)
 

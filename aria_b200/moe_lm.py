@@ -15,8 +15,8 @@ argument meaning as the reference; the arithmetic is ours.
     AriaMoELMModel        moe_lm.py:605-636    AriaMoELMModel
     AriaMoELMForCausalLM  moe_lm.py:639-679    AriaMoELMForCausalLM
 
-Inference (eval-mode routing, moe_lm.py:261-269) only in this round; the training-only aux/z losses
-(moe_lm.py:84-166) are out of scope (SURVEY.md §8 a3').  There is no CPU fallback.
+These modules are the inference path (eval-mode routing, moe_lm.py:261-269); the differentiable MoE block incl. the
+training-mode aux/z losses (moe_lm.py:84-166) lives in aria_b200/moe_train.py.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -97,9 +97,18 @@ class TopKRouter(nn.Module):
         super().__init__()
         self.config = config
         self.weight = _param(config.moe_num_experts, config.hidden_size, device=device)
+        # Parity / replay hook: when set to an int32 CUDA tensor [T, k], the expert choice of the next forward() is TAKEN
+        # from it (scores and counts are still computed on the device from this router's own logits).  The forced-routing
+        # parity test injects the oracle's top-k here so that a bf16 near-tie in the router cannot mask other differences.
+        self.forced_top_indices: Optional[torch.Tensor] = None
 
     def forward(self, input: torch.Tensor):
         x = input.reshape(-1, input.shape[-1])
+        if self.forced_top_indices is not None:
+            logits = ops.linear(x, self.weight)                                   # gating, moe_lm.py:200
+            top_indices = self.forced_top_indices
+            scores, tokens_per_expert = ops.route_given_indices(logits, top_indices)
+            return scores, top_indices, tokens_per_expert
         scores, top_indices, tokens_per_expert, _ = ops.router_topk(x, self.weight, self.config.moe_topk)
         return scores, top_indices, tokens_per_expert
 
@@ -136,8 +145,8 @@ def _as_offsets(tokens_per_expert: torch.Tensor, num_experts: int, device) -> to
     CUDA) or our int32 device row offsets [E+1] (TokenDispatcher.expert_offsets)."""
     t = tokens_per_expert
     if t.numel() == num_experts + 1:
-        if not (t.dtype == torch.int32 and t.is_cuda):
-            raise RuntimeError("row offsets must be an int32 CUDA tensor of E+1 entries")
+        if t.dtype != torch.int32:      # (CUDA residency is enforced where the pointer is taken, ops._chk)
+            raise RuntimeError("row offsets must be an int32 tensor of E+1 entries")
         return t
     if t.numel() != num_experts:
         raise RuntimeError(f"tokens_per_expert must have {num_experts} (counts) or {num_experts + 1} (offsets) entries")
@@ -258,21 +267,26 @@ class AriaAttention(nn.Module):
         self.v_proj = Linear(d, d, device=device)
         self.o_proj = Linear(d, d, device=device)
 
-    def forward(self, hidden_states, cache: KVCache, rope, residual=None):
+    def forward(self, hidden_states, cache: KVCache, rope, residual=None, key_mask=None, position_ids=None):
+        """key_mask [B, pos0+T] uint8, 1 = key masked out (padded batch); position_ids [B*T] int32 RoPE positions
+        (default: cache position pos0 + t, what LlamaModel uses when none are given)."""
         B, T, d = hidden_states.shape
         H, hd = self.num_heads, self.head_dim
         pos0 = cache.seq_len
+        if pos0 + T > cache.T_max:
+            # the fused epilogue stores k/v rows at pos0 + t and reads the RoPE table there: never past the cache
+            raise RuntimeError(f"KV cache overflow: {pos0} cached + {T} new tokens > T_max = {cache.T_max}")
         kc, vc = cache.k[self.layer_idx], cache.v[self.layer_idx]
         q = cache.q  # staging buffer with the cache's strides: the fused epilogue scatters q, k, v with one stride pair
         cos, sin = rope
         ops.qkv_heads(hidden_states, [self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], [None] * 3,
-                      [q, kc, vc], hd, T, pos0=pos0, rope_mask=0b011, rope_cos=cos, rope_sin=sin)
+                      [q, kc, vc], hd, T, pos0=pos0, rope_mask=0b011, rope_cos=cos, rope_sin=sin, position_ids=position_ids)
         Tk = pos0 + T
         scale = hd ** -0.5
         if T == 1:
-            o = ops.attention_decode(q[:, :, pos0, :], kc, vc, Tk, scale).view(B, 1, d)  # strided view, no copy
-        else:
-            o = ops.attention(q[:, :, pos0:], kc, vc, T, Tk, scale, causal=True)
+            o = ops.attention_decode(q[:, :, pos0, :], kc, vc, Tk, scale, key_mask=key_mask).view(B, 1, d)  # strided view, no copy
+        else:  # prefill, or a multi-token continuation (chunked prefill): the queries are the last T of Tk positions
+            o = ops.attention(q[:, :, pos0:], kc, vc, T, Tk, scale, causal=True, key_mask=key_mask)
         return ops.linear(o, self.o_proj.weight, residual=residual)
 
 
@@ -288,13 +302,13 @@ class MoEDecoderLayer(nn.Module):
         self.input_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, device)
         self.post_attention_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, device)
 
-    def forward(self, x, pending, cache, rope):
+    def forward(self, x, pending, cache, rope, key_mask=None, position_ids=None):
         """x: residual stream; pending: MoE output of the previous layer not yet added (or None)."""
         if pending is None:
             h = self.input_layernorm(x)
         else:
             h, x = self.input_layernorm(x, residual=pending)
-        x = self.self_attn(h, cache, rope, residual=x)
+        x = self.self_attn(h, cache, rope, residual=x, key_mask=key_mask, position_ids=position_ids)
         h = self.post_attention_layernorm(x)
         return x, self.mlp(h)
 
@@ -319,12 +333,14 @@ class AriaMoELMModel(nn.Module):
             self._rope = ops.rope_table(inv_freq.to(device), n_pos)
         return self._rope
 
-    def forward(self, inputs_embeds, cache: KVCache):
+    def forward(self, inputs_embeds, cache: KVCache, key_mask=None, position_ids=None):
         B, T, _ = inputs_embeds.shape
+        if cache.seq_len + T > cache.T_max:
+            raise RuntimeError(f"KV cache overflow: {cache.seq_len} cached + {T} new tokens > T_max = {cache.T_max}")
         rope = self.rope_tables(cache.T_max, inputs_embeds.device)
         x, pending = inputs_embeds, None
         for layer in self.layers:
-            x, pending = layer(x, pending, cache, rope)
+            x, pending = layer(x, pending, cache, rope, key_mask, position_ids)
         cache.seq_len += T
         return x, pending  # final residual add happens inside the final norm
 
@@ -362,11 +378,12 @@ class AriaMoELMForCausalLM(nn.Module):
     def set_output_embeddings(self, value):
         self.lm_head = value
 
-    def forward(self, inputs_embeds, cache: Optional[KVCache] = None, num_logits_to_keep: int = 0):
+    def forward(self, inputs_embeds, cache: Optional[KVCache] = None, num_logits_to_keep: int = 0, key_mask=None,
+                position_ids=None):
         B, T, _ = inputs_embeds.shape
         if cache is None:
             cache = self.new_cache(B, T, inputs_embeds.device)
-        x, pending = self.model(inputs_embeds, cache)
+        x, pending = self.model(inputs_embeds, cache, key_mask, position_ids)
         if num_logits_to_keep:
             x = x[:, -num_logits_to_keep:, :].contiguous()
             pending = pending[:, -num_logits_to_keep:, :].contiguous()

@@ -328,6 +328,20 @@ def route_from_logits(logits: torch.Tensor, k: int):
     return scores, idx, counts
 
 
+def route_given_indices(logits: torch.Tensor, top_idx: torch.Tensor):
+    """Scores / counts for a GIVEN expert choice (parity / replay hook; see include/aria_b200.h)."""
+    _chk(logits), _chk(top_idx, torch.int32)
+    T, E = logits.shape
+    k = top_idx.shape[1]
+    assert top_idx.shape[0] == T
+    scores = torch.empty((T, k), dtype=bf16, device=logits.device)
+    counts = torch.empty((E,), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        L.check(L.load().aria_route_given_indices(_p(logits), _p(top_idx), _p(scores), _p(counts), T, E, k, _stream(logits)),
+                "route_given_indices")
+    return scores, counts
+
+
 def build_permutation(top_idx: torch.Tensor, counts: torch.Tensor, row_align: int = 1):
     """row_align=16 (training): expert blocks start on multiples of 16 rows; `src` then has T*k + E*15 slots (upper bound
     of the padded row count, the true total is offsets[E]) and pad rows carry -1."""
@@ -460,10 +474,14 @@ def add_pos_embedding(x: torch.Tensor, pos_ids: torch.Tensor, table: torch.Tenso
 # ------------------------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tq: int, Tk: int, scale: float, causal: bool,
               out_hd: int = 128, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B,H,>=Tq,128], k/v [B,H,>=Tk,128] head-major (first Tq/Tk rows used) -> out [B, Tq, H*out_hd]."""
-    _chk(q), _chk(k), _chk(v)
+    """q [B,H,>=Tq,128], k/v [B,H,>=Tk,128] head-major (first Tq/Tk rows used) -> out [B, Tq, H*out_hd].
+    Token rows must be 128 contiguous bf16 at a row stride of 128 (a slice q[:, :, pos0:] of a staging buffer is fine)."""
+    for t in (q, k, v):
+        if not (t.is_cuda and t.dtype == bf16 and t.dim() == 4 and t.stride(-1) == 1 and t.stride(-2) == 128 and t.data_ptr() % 16 == 0):
+            raise RuntimeError("attention: q/k/v must be CUDA bf16 [B,H,T,128] with 128-element token rows (16-byte aligned)")
     B, H = q.shape[0], q.shape[1]
     assert q.shape[-1] == 128 and k.shape[-1] == 128 and k.stride() == v.stride()
+    assert q.shape[2] >= Tq and k.shape[2] >= Tk
     out = torch.empty((B, Tq, H * out_hd), dtype=bf16, device=q.device)
     if key_mask is not None:
         _chk(key_mask, torch.uint8)
@@ -474,9 +492,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tq: int, Tk: in
     return out
 
 
-def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tk: int, scale: float) -> torch.Tensor:
+def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tk: int, scale: float,
+                     key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B,H,128] (any strides with a contiguous last dim, e.g. a row of the q staging buffer), cache k/v
-    [B,H,T_max,128] -> out [B, H*128]."""
+    [B,H,T_max,128] -> out [B, H*128].  key_mask [B, Tk] uint8, 1 = masked out (padded batch)."""
     _chk(k), _chk(v)
     if not (q.is_cuda and q.dtype == bf16 and q.stride(-1) == 1 and q.data_ptr() % 8 == 0):
         raise RuntimeError("attention_decode: q must be a CUDA bf16 tensor with a contiguous last dim")
@@ -485,7 +504,10 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tk: int,
     ws_bytes = lib.aria_attention_decode_workspace_bytes(B, H, Tk)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
     out = torch.empty((B, H * 128), dtype=bf16, device=q.device)
+    if key_mask is not None:
+        _chk(key_mask, torch.uint8)
+        assert key_mask.shape == (B, Tk)
     with torch.cuda.device(q.device):
-        L.check(lib.aria_attention_decode(_p(q), _p(k), _p(v), _p(out), B, H, Tk, q.stride(0), q.stride(1), k.stride(0),
+        L.check(lib.aria_attention_decode(_p(q), _p(k), _p(v), _p(out), _p(key_mask), B, H, Tk, q.stride(0), q.stride(1), k.stride(0),
                                           k.stride(1), scale, _p(ws), ws_bytes, _stream(q)), "attention_decode")
     return out

@@ -70,31 +70,49 @@ class Idefics2VisionEmbeddings(nn.Module):
         self.num_patches_per_side = cfg.image_size // cfg.patch_size
         self.position_embedding = nn.Embedding(self.num_patches_per_side ** 2, cfg.hidden_size, device=device, dtype=bf16)
         self.position_embedding.weight.requires_grad_(False)
+        self._bucket_cache = {}
+        self._full_ids = None
 
-    def position_ids(self, patch_attention_mask: torch.Tensor, dtype) -> torch.Tensor:
-        """NaViT bucketised fractional coordinates (transformers Idefics2VisionEmbeddings.forward) — a few
-        [B, 70]-sized integer ops; index glue, kept in torch on the device."""
-        pm = patch_attention_mask
-        B, Hp, Wp = pm.shape
-        dev = pm.device
+    def _buckets(self, nb: int) -> torch.Tensor:
+        """Bucket index of each of `nb` valid rows (or columns): Idefics2VisionEmbeddings.forward of the transformers release the
+        reference pins (4.46.3, pyproject.toml:13) — `bucketize(arange(0, 1 - 1e-6, 1 / nb), boundaries, right=True)` with fp32
+        coordinates computed on the HOST.  When nb == num_patches_per_side every coordinate sits on a boundary up to fp32
+        rounding, so the result depends on the exact arithmetic: this runs the very same torch CPU ops (host-side index glue,
+        a few hundred bytes, cached per nb).  (transformers 5.x casts the coordinates to the pixel dtype first — bf16 moves
+        half of the 70 buckets by one; a real checkpoint was trained with the fp32 ids.)"""
+        t = self._bucket_cache.get(nb)
+        if t is None:
+            n = self.num_patches_per_side
+            boundaries = torch.arange(1 / n, 1.0, 1 / n)
+            step = 1 / torch.tensor(nb)                       # fp32 tensor, as `1 / nb_patches_h` is in the reference
+            t = torch.bucketize(torch.arange(0, 1 - 1e-6, step), boundaries, right=True)
+            self._bucket_cache[nb] = t
+        return t
+
+    def position_ids(self, patch_mask_host: Optional[torch.Tensor], B: int, device) -> torch.Tensor:
+        """patch_mask_host: None (every patch valid) or the [B, Hp, Wp] bool patch mask ON THE HOST -> [B*Hp*Wp] int64 ids
+        on `device`.  Follows the reference loop: ids of the nb_h x nb_w valid grid are written to the mask's True positions."""
         n = self.num_patches_per_side
-        boundaries = torch.arange(1 / n, 1.0, 1 / n, device=dev)
-        nb_h = pm[:, :, 0].sum(dim=1)
-        nb_w = pm[:, 0, :].sum(dim=1)
-        fh = torch.arange(Hp, device=dev, dtype=torch.float32)[None, :] * (1.0 / nb_h)[:, None]
-        fw = torch.arange(Wp, device=dev, dtype=torch.float32)[None, :] * (1.0 / nb_w)[:, None]
-        fh = torch.clamp(fh, max=1.0 - 1e-6).to(dtype)
-        fw = torch.clamp(fw, max=1.0 - 1e-6).to(dtype)
-        bh = torch.bucketize(fh, boundaries, right=True)
-        bw = torch.bucketize(fw, boundaries, right=True)
-        ids = (bh[:, :, None] * n + bw[:, None, :]).reshape(B, -1)
-        return torch.where(pm.view(B, -1), ids, torch.zeros_like(ids))
+        if patch_mask_host is None:
+            key = (B, str(device))
+            if self._full_ids is None or self._full_ids[0] != key:
+                b = self._buckets(n)
+                ids = (b[:, None] * n + b[None, :]).flatten()
+                self._full_ids = (key, ids.repeat(B).to(device))
+            return self._full_ids[1]
+        pm = patch_mask_host
+        pos = torch.zeros(B, pm.shape[1] * pm.shape[2], dtype=torch.int64)
+        for b in range(B):
+            nb_h, nb_w = int(pm[b, :, 0].sum()), int(pm[b, 0, :].sum())
+            ids = (self._buckets(nb_h)[:, None] * n + self._buckets(nb_w)[None, :]).flatten()
+            pos[b][pm[b].reshape(-1)] = ids      # raises on a non-rectangular mask, like the reference
+        return pos.reshape(-1).to(device, non_blocking=True)
 
-    def forward(self, pixel_values, patch_attention_mask):
+    def forward(self, pixel_values, patch_mask_host):
         w = self.patch_embedding.packed_weight()
         patches = ops.im2col_patches(pixel_values, self.cfg.patch_size, w.shape[1])
         x = ops.linear(patches, w, self.patch_embedding.bias)
-        pos = self.position_ids(patch_attention_mask, pixel_values.dtype).reshape(-1).contiguous()
+        pos = self.position_ids(patch_mask_host, pixel_values.shape[0], pixel_values.device)
         x = ops.add_pos_embedding(x, pos, self.position_embedding.weight)
         return x.view(pixel_values.shape[0], -1, x.shape[-1])
 
@@ -156,17 +174,17 @@ class AriaVisionTransformer(nn.Module):
         self.embeddings = Idefics2VisionEmbeddings(cfg, device)
         self.encoder = Idefics2Encoder(cfg, device)
 
-    def forward(self, pixel_values, patch_attention_mask, all_valid: Optional[bool] = None):
-        """all_valid: host-side knowledge that no patch is padded (skips a device->host sync)."""
+    def forward(self, pixel_values, patch_mask_host: Optional[torch.Tensor] = None):
+        """patch_mask_host: None = every patch valid; else the [B, Hp, Wp] bool patch mask on the HOST (position ids and the
+        "is anything padded" branch are host-side index glue, as in the reference's per-image loop)."""
         B = pixel_values.shape[0]
-        x = self.embeddings(pixel_values, patch_attention_mask)
+        if patch_mask_host is not None and bool(patch_mask_host.all()):
+            patch_mask_host = None
+        x = self.embeddings(pixel_values, patch_mask_host)
         N = x.shape[1]
-        flat = patch_attention_mask.view(B, -1)
         key_mask = None
-        if all_valid is None:
-            all_valid = bool(flat.all())  # same data-dependent branch as the HF mask creation (one sync)
-        if not all_valid:
-            key_mask = (~flat).to(torch.uint8).contiguous()
+        if patch_mask_host is not None:
+            key_mask = (~patch_mask_host.reshape(B, -1)).to(torch.uint8).to(x.device, non_blocking=True).contiguous()
         H = self.config.num_attention_heads
         qkv = [torch.zeros(B, H, N, 128, dtype=bf16, device=x.device) for _ in range(3)]
         for layer in self.encoder.layers:
@@ -184,22 +202,14 @@ class AriaVisionModel(nn.Module):
         self.vision_model = AriaVisionTransformer(cfg, device)
 
     def forward(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None):
-        P = self.config.patch_size
-        B = pixel_values.shape[0]
         if pixel_mask is None:
-            pam = torch.ones(B, pixel_values.shape[2] // P, pixel_values.shape[3] // P, dtype=torch.bool,
-                             device=pixel_values.device)
-            image_atts = None
-            all_valid = True
-        else:
-            all_valid = None
-            if not pixel_mask.is_cuda:  # host mask (the e2e path): decide on the host, no device sync
-                all_valid = bool(self._create_patch_attention_mask(pixel_mask).all())
-                pixel_mask = pixel_mask.to(pixel_values.device, non_blocking=True)
-            pam = self._create_patch_attention_mask(pixel_mask)
-            image_atts = torch.logical_not(pam.flatten(1))  # vision_encoder.py:147-152
-        out = self.vision_model(pixel_values, pam, all_valid)
-        return out, image_atts
+            return self.vision_model(pixel_values, None), None
+        # the patch mask is [B, 70, 70] bools: built where the pixel mask lives, used on the host (a device-resident mask costs
+        # one small D2H copy — the reference syncs here too, `p_attn_mask.view(-1).cpu()` per image)
+        pam = self._create_patch_attention_mask(pixel_mask)
+        pam_host = pam.cpu() if pam.is_cuda else pam
+        image_atts = torch.logical_not(pam_host.flatten(1)).to(pixel_values.device, non_blocking=True)  # vision_encoder.py:147-152
+        return self.vision_model(pixel_values, pam_host), image_atts
 
     def _create_patch_attention_mask(self, pixel_mask):
         """vision_encoder.py:132-145 (bool glue on a [B,S,S] mask)."""

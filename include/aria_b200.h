@@ -115,6 +115,12 @@ int aria_router_topk(const void* x, const void* w_router, void* logits_out, int3
 int aria_route_from_logits(const void* logits, int32_t* top_idx, void* scores, int32_t* counts, int64_t T,
                            int32_t E, int32_t k, aria_stream_t stream);
 
+/* Routing with the expert choice GIVEN (parity / replay hook): top_idx [T, k] int32 is an INPUT; scores = fp32 softmax over the
+ * logits at those ids (same arithmetic as above), counts = their histogram.  Lets a test inject the oracle's top-k into the
+ * CUDA path so that bf16 near-ties in the router cannot hide other differences. */
+int aria_route_given_indices(const void* logits, const int32_t* top_idx, void* scores, int32_t* counts, int64_t T,
+                             int32_t E, int32_t k, aria_stream_t stream);
+
 /* TokenDispatcher.token_permutation (moe_lm.py:313-334): stable counting sort of the T*k expert ids.
  *   offsets [E+1] int32 (exclusive scan of counts), dest_row [T*k] int32 (row of flattened (token,slot) in
  *   the expert-sorted order == inverse of the reference's `sorted_indices`), src_token [T*k] int32 (token of
@@ -220,8 +226,9 @@ int aria_attention_fwd(const void* q, const void* k, const void* v, void* out, c
                        int64_t kv_stride_b, int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal,
                        aria_stream_t stream);
 /* Single-token decode against a KV cache (HBM-bound, split-KV): q element (b,h,:) at q + b*q_stride_b + h*q_stride_h
- * (128 contiguous bf16), cache [B,H,Tk_max,128], out [B, H*128].  workspace: B*H*splits*(128+2) floats. */
-int aria_attention_decode(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tk,
+ * (128 contiguous bf16), cache [B,H,Tk_max,128], out [B, H*128].  workspace: B*H*splits*(128+2) floats.
+ * key_mask [B, Tk] uint8 or NULL: 1 = key is masked OUT (padded batch: the HF 2-D attention_mask inverted). */
+int aria_attention_decode(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask, int32_t B, int32_t H, int32_t Tk,
                           int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b, int64_t kv_stride_h, float scale,
                           void* workspace, int64_t workspace_bytes, aria_stream_t stream);
 int64_t aria_attention_decode_workspace_bytes(int32_t B, int32_t H, int32_t Tk);

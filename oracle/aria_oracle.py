@@ -303,22 +303,23 @@ def patch_attention_mask(pixel_mask: Tensor, patch: int) -> Tensor:
     return (sub.sum(dim=(-1, -2)) > 0).bool()
 
 
-def vit_position_ids(pmask: Tensor, n_side: int, dtype) -> Tensor:
-    """Idefics2VisionEmbeddings.forward: NaViT bucketised fractional coordinates -> position ids."""
+def vit_position_ids(pmask: Tensor, n_side: int) -> Tensor:
+    """Idefics2VisionEmbeddings.forward of transformers 4.46.3 (the release the reference pins, pyproject.toml:13): per image,
+    fp32 fractional coordinates `arange(0, 1 - 1e-6, 1 / nb)` bucketised against `arange(1/n, 1, 1/n)` (right=True), ids of
+    the nb_h x nb_w valid grid written to the True positions of the patch mask.  (transformers 5.x casts the coordinates to
+    the pixel dtype before bucketising; in bf16 that shifts about half of the 70 buckets by one, so it is NOT what a
+    checkpoint trained under 4.46.3 saw.)"""
     B, Hp, Wp = pmask.shape
     boundaries = torch.arange(1 / n_side, 1.0, 1 / n_side)
     pos = torch.zeros(B, Hp * Wp, dtype=torch.long)
-    nb_h = pmask[:, :, 0].sum(dim=1)
-    nb_w = pmask[:, 0, :].sum(dim=1)
-    fh = torch.arange(Hp, dtype=torch.float32)[None, :] * (1.0 / nb_h)[:, None]
-    fw = torch.arange(Wp, dtype=torch.float32)[None, :] * (1.0 / nb_w)[:, None]
-    fh = torch.clamp(fh, max=1.0 - 1e-6).to(dtype)
-    fw = torch.clamp(fw, max=1.0 - 1e-6).to(dtype)
-    bh = torch.bucketize(fh, boundaries, right=True)
-    bw = torch.bucketize(fw, boundaries, right=True)
-    ids = (bh[:, :, None] * n_side + bw[:, None, :]).reshape(B, -1)
-    flat = pmask.view(B, -1)
-    pos[flat] = ids[flat]
+    for b in range(B):
+        p = pmask[b]
+        nb_h, nb_w = p[:, 0].sum(), p[0].sum()
+        fh = torch.arange(0, 1 - 1e-6, 1 / nb_h)
+        fw = torch.arange(0, 1 - 1e-6, 1 / nb_w)
+        bh = torch.bucketize(fh, boundaries, right=True)
+        bw = torch.bucketize(fw, boundaries, right=True)
+        pos[b][p.reshape(-1)] = (bh[:, None] * n_side + bw).flatten()
     return pos
 
 
@@ -328,7 +329,7 @@ def vit_embeddings(pixel_values: Tensor, pmask: Tensor, w: Dict[str, Tensor], vc
     x = F.conv2d(pixel_values, w[prefix + "embeddings.patch_embedding.weight"],
                  w[prefix + "embeddings.patch_embedding.bias"], stride=P)
     x = x.flatten(2).transpose(1, 2)
-    pos = vit_position_ids(pmask, vcfg["image_size"] // P, pixel_values.dtype)
+    pos = vit_position_ids(pmask, vcfg["image_size"] // P)
     return x + F.embedding(pos, w[prefix + "embeddings.position_embedding.weight"])
 
 

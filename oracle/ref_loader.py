@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference modules from /root/reference (build container) or from
+oracle/_ref/ (the same files staged byte-for-byte by oracle/build_ref.py; this is what the GPU box has).
 
-Used only by `oracle/make_golden.py` (golden-vector generation, in the build container) and by
-`tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent, e.g. on the GPU box).
-Nothing in `aria_b200/` may import this file.
+Used by `oracle/make_golden.py` (golden-vector generation), `tests/test_oracle_vs_reference.py`, the drop-in GPU tests
+(tests/test_gpu_dropin.py: our seams installed on the reference's own classes) and `bench.py --impl reference` / its
+`cpu_baseline` leg (the reference's CPU forward, kind "reference").  Nothing in `aria_b200/` may import this file.
 
 Harness: the reference package cannot be imported as a package under the installed
 transformers 5.5 (`aria/model/__init__.py` pulls in processors whose imports moved), so we
@@ -20,7 +21,10 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("ARIA_REFERENCE_ROOT", "/root/reference")
+# the mounted reference when present (build container), else the files staged byte-for-byte by oracle/build_ref.py
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = os.environ.get("ARIA_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/aria/model/moe_lm.py") else _STAGED)
 
 
 def reference_available() -> bool:

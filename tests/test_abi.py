@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_version_and_arch(lib):
-    assert lib.aria_abi_version() == 1
+    assert lib.aria_abi_version() == 2
     assert lib.aria_build_arch() == b"sm_100a"
 
 

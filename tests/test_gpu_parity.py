@@ -377,3 +377,25 @@ def test_graphed_prefill_equals_eager():
     bad[0, 5] = 11
     with pytest.raises(ValueError):
         g(bad, pv)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices():
+    """The reference can span GPUs inside ONE process (`device_map="auto"`, aria/inference.py:55-57; hence the
+    `torch.cuda.set_device(input.device)` at moe_lm.py:483).  Every C-ABI call must honour the tensor's device: the
+    dynamic-shared-memory opt-ins and the SM count are per-device state inside the library."""
+    from aria_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 512, generator=g).bfloat16()
+    w = (torch.randn(384, 512, generator=g) * 0.05).bfloat16()
+    q = torch.randn(1, 2, 200, 128, generator=g).bfloat16()
+    ref = x.float() @ w.float().t()
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        y = ops.linear(x.to(dev), w.to(dev))
+        o = ops.attention(q.to(dev), q.to(dev), q.to(dev), 200, 200, 128 ** -0.5, True)
+        torch.cuda.synchronize(dev)
+        assert y.device == torch.device(dev)
+        assert float((y.float().cpu() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+        outs.append(o.float().cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

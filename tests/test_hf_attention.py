@@ -31,7 +31,7 @@ def test_unsupported_arguments_fail_loudly():
     with pytest.raises(NotImplementedError):
         f(_Stub(), q, q, q, None, dropout=0.1)
     with pytest.raises(NotImplementedError):
-        f(_Stub(), q, q, q, torch.ones(1, 4, dtype=torch.bool))
+        f(_Stub(), q, q, q, torch.ones(1, 1, 4, dtype=torch.bool))     # neither the 2-D padding mask nor a 4-D mask
     with pytest.raises(NotImplementedError):
         f(_Stub(), q, q[:, :1], q[:, :1], None)
     with pytest.raises(NotImplementedError):
