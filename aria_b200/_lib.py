@@ -77,7 +77,8 @@ SIGNATURES = {
     "aria_peer_barrier": (i32, [vp, i32, i32, vp, vp]),
     "aria_ep_layout": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
     "aria_scatter_rows_grouped": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, i64, vp]),
-    "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),
+    "aria_attention_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp, i64, vp]),
+    "aria_attention_fwd_workspace_bytes": (i64, [i32, i32, i32, i32, i32, i32]),
     "aria_attention_decode": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i64, vp]),
     "aria_attention_decode_workspace_bytes": (i64, [i32, i32, i32]),
 }
@@ -95,7 +96,7 @@ def load():
             f"{LIB_PATH} not found: build it with `python -m aria_b200.build` (nvcc, sm_100a). "
             "aria_b200 has no CPU/eager fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(EXTRA_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
@@ -105,6 +106,10 @@ def load():
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; memsets are not counted)
 KERNELS_PER_CALL = {"router_topk": 2, "attention_decode": 2}
+# kernels exported for A/B measurements only (scripts/), not part of include/aria_b200.h
+EXTRA_SIGNATURES = {
+    "aria_attention_fwd_v2": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),
+}
 launch_count = 0
 
 

@@ -1,6 +1,9 @@
 // Attention for sm_100a.
 //
-// aria_attention_fwd: flash-style forward with both contractions on tcgen05 tensor cores:
+// NOTE (round 2): `aria_attention_fwd` now lives in attention_v3.cu.  The round-1 kernel below stays exported as
+// `aria_attention_fwd_v2` (not part of the C ABI in include/) for A/B timing in scripts/; the decode kernels are current.
+//
+// aria_attention_fwd_v2: flash-style forward with both contractions on tcgen05 tensor cores:
 //     S = Q K^T   (A = Q tile, B = K tile, both K-major SW128 in shared memory, accumulator S in TMEM)
 //     O += P V    (A = P, bf16, written by the softmax warps back into TMEM over S and consumed straight from
 //                  TMEM; B = V tile consumed MN-major — V is [keys, d] with d contiguous, exactly the HF cache
@@ -433,7 +436,7 @@ static int make_tmap_heads(CUtensorMap* tm, const void* ptr, int T, int H, int B
 
 using namespace aria;
 
-extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask, int32_t B,
+extern "C" int aria_attention_fwd_v2(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask, int32_t B,
                                   int32_t H, int32_t Tq, int32_t Tk, int64_t q_stride_b, int64_t q_stride_h,
                                   int64_t kv_stride_b, int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal,
                                   aria_stream_t stream_) {

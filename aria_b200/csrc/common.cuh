@@ -43,10 +43,16 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost-first; strides[i] is the byte stride
+// bf16 tensor map, 128B swizzle (or the given one), zero OOB fill.  dims/strides innermost-first; strides[i] is the byte stride
 // of dim i+1 (rank-1 entries).
+inline int make_tmap_bf16_swz(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box, CUtensorMapSwizzle swizzle);
 inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box) {
+  return make_tmap_bf16_swz(tm, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+inline int make_tmap_bf16_swz(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box, CUtensorMapSwizzle swizzle) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     fprintf(stderr, "aria_b200: cuTensorMapEncodeTiled unavailable\n");
@@ -72,12 +78,12 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* ptr, int rank, const uint
     ctx_bound = true;
   }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {  // e.g. the context was popped by another library
     cudaFree(0);
     r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) {

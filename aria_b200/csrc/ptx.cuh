@@ -175,6 +175,14 @@ ARIA_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+ARIA_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 ARIA_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 ARIA_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -286,6 +294,20 @@ ARIA_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// Same with an explicit swizzle mode (descriptor bits [61,64)): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+//   SWIZZLE_32B K-major  tile [rows][16 bf16] (TMA box {16, rows}, CU_TENSOR_MAP_SWIZZLE_32B): SBO = 256 (8 rows x 32 B).
+//   SWIZZLE_32B MN-major tile [k rows][16 bf16 of MN] per 16-wide chunk: SBO = 256 (8 k-rows), LBO = chunk stride,
+//            advancing K by 16 rows = +512 B.
+constexpr uint32_t UMMA_SW128 = 2, UMMA_SW64 = 4, UMMA_SW32 = 6;
+ARIA_DEVICE uint64_t make_smem_desc_sw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(swizzle) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                       // D format: F32
@@ -295,6 +317,75 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          | ((b_mn_major ? 1u : 0u) << 16)
          | (static_cast<uint32_t>(N >> 3) << 17)
          | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- warp-specialised register budgets
+template <int N> ARIA_DEVICE void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> ARIA_DEVICE void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2)
+// One instruction, two fp32 lanes held in a 64-bit register pair: halves the FMA-pipe slots of the softmax inner loop.
+ARIA_DEVICE uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+ARIA_DEVICE uint64_t pack_u2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+ARIA_DEVICE void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+ARIA_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+ARIA_DEVICE uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+ARIA_DEVICE uint64_t add2_rm(uint64_t a, uint64_t b) {  // round towards -inf: floor() of the magic-number trick
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+ARIA_DEVICE uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+ARIA_DEVICE float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for two values on the FMA / ALU pipes only (no MUFU): Cody-Waite split with the round-down magic-number trick and a
+// degree-3 minimax polynomial on the fraction (max rel. error ~9e-5, far below the bf16 rounding of P that follows) — the
+// FlashAttention-4 way of taking exponentials off the 16-per-clock MUFU unit.  x must be <= 0-ish (no overflow handling);
+// x < -125 (incl. -inf of masked keys) is clamped: the result is then ~2^-125, i.e. zero for every purpose here.
+ARIA_DEVICE uint64_t exp2_poly2(uint64_t x) {
+  float x0, x1;
+  unpack_f2(x, x0, x1);
+  x = pack_f2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t magic = pack_f2(12582912.f, 12582912.f);       // 1.5 * 2^23: floor(x) lands in the low mantissa bits
+  const uint64_t r = add2_rm(x, magic);
+  const uint64_t fl = add2(r, pack_f2(-12582912.f, -12582912.f));  // floor(x) as a float (exact)
+  float f0, f1, g0, g1;
+  unpack_f2(x, f0, f1);
+  unpack_f2(fl, g0, g1);
+  const uint64_t fr = pack_f2(f0 - g0, f1 - g1);                 // fraction in [0, 1)
+  uint64_t p = fma2(fr, pack_f2(0.077119089663028717f, 0.077119089663028717f), pack_f2(0.227564394474029541f, 0.227564394474029541f));
+  p = fma2(p, fr, pack_f2(0.695146143436431885f, 0.695146143436431885f));
+  p = fma2(p, fr, pack_f2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack_f2(p, p0, p1);
+  unpack_f2(r, r0, r1);
+  // exponent: add floor(x) (low bits of r) << 23 to the bit pattern of the polynomial value
+  const uint32_t o0 = __float_as_uint(p0) + (__float_as_uint(r0) << 23);
+  const uint32_t o1 = __float_as_uint(p1) + (__float_as_uint(r1) << 23);
+  return pack_u2(o0, o1);
 }
 
 // ---------------------------------------------------------------- small numeric helpers

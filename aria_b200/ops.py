@@ -23,15 +23,15 @@ def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def _chk(t: torch.Tensor, dtype=bf16):
+def _chk(t: torch.Tensor, dtype=bf16, align: int = 16):
     if not t.is_cuda:
         raise RuntimeError("aria_b200 ops need CUDA tensors (there is no CPU path)")
     if t.dtype != dtype:
         raise RuntimeError(f"expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError("expected a contiguous tensor")
-    if t.data_ptr() % 16:
-        raise RuntimeError("expected 16-byte aligned storage")
+    if t.data_ptr() % align:
+        raise RuntimeError(f"expected {align}-byte aligned storage")
     return t
 
 
@@ -432,7 +432,7 @@ def rope_table(inv_freq: torch.Tensor, n_pos: int):
 
 
 def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
-    _chk(ids, torch.int64), _chk(table)
+    _chk(ids, torch.int64, align=8), _chk(table)      # ids are read element-wise (a [1, 1] slice of a longer id row is fine)
     out = torch.empty((*ids.shape, table.shape[1]), dtype=bf16, device=table.device)
     with torch.cuda.device(table.device):
         L.check(L.load().aria_embedding(_p(ids), _p(table), _p(out), ids.numel(), table.shape[1], _stream(table)), "embedding")
@@ -442,7 +442,7 @@ def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 def merge_image_features(ids: torch.Tensor, image_token: int, features: torch.Tensor, embeds: torch.Tensor,
                          count_out: Optional[torch.Tensor] = None):
     """In place: embeds rows at <|img|> positions <- consecutive rows of features (masked_scatter)."""
-    _chk(ids, torch.int64), _chk(features), _chk(embeds)
+    _chk(ids, torch.int64, align=8), _chk(features), _chk(embeds)
     d = embeds.shape[-1]
     with torch.cuda.device(embeds.device):
         L.check(L.load().aria_merge_image_features(_p(ids), image_token, _p(features), _p(embeds), _p(count_out),
@@ -486,9 +486,25 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, Tq: int, Tk: in
     if key_mask is not None:
         _chk(key_mask, torch.uint8)
         assert key_mask.shape == (B, Tk)
+    lib = L.load()
+    ws, ws_bytes = None, 0
+    if not causal:  # persistent launch: scratch for the stream-K pieces of the leftover units (see include/aria_b200.h)
+        ws_bytes = lib.aria_attention_fwd_workspace_bytes(B, H, Tq, Tk, out_hd, 0)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
-        L.check(L.load().aria_attention_fwd(_p(q), _p(k), _p(v), _p(out), _p(key_mask), B, H, Tq, Tk, q.stride(0), q.stride(1),
-                                            k.stride(0), k.stride(1), out_hd, scale, int(causal), _stream(q)), "attention_fwd")
+        L.check(lib.aria_attention_fwd(_p(q), _p(k), _p(v), _p(out), _p(key_mask), B, H, Tq, Tk, q.stride(0), q.stride(1),
+                                       k.stride(0), k.stride(1), out_hd, scale, int(causal), _p(ws), ws_bytes, _stream(q)),
+                "attention_fwd")
+    return out
+
+
+def attention_v2(q, k, v, Tq, Tk, scale, causal, out_hd=128, key_mask=None):
+    """Round-1 kernel (aria_attention_fwd_v2), kept for A/B timing in scripts/ only."""
+    B, H = q.shape[0], q.shape[1]
+    out = torch.empty((B, Tq, H * out_hd), dtype=bf16, device=q.device)
+    with torch.cuda.device(q.device):
+        L.check(L.load().aria_attention_fwd_v2(_p(q), _p(k), _p(v), _p(out), _p(key_mask), B, H, Tq, Tk, q.stride(0), q.stride(1),
+                                               k.stride(0), k.stride(1), out_hd, scale, int(causal), _stream(q)), "attention_fwd")
     return out
 
 

@@ -224,7 +224,11 @@ int aria_scatter_rows_grouped(const void* rows, const int32_t* src_token, const 
 int aria_attention_fwd(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask,
                        int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t q_stride_b, int64_t q_stride_h,
                        int64_t kv_stride_b, int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal,
-                       aria_stream_t stream);
+                       void* workspace, int64_t workspace_bytes, aria_stream_t stream);
+/* Scratch for the stream-K pieces of a persistent (non-causal) launch: when there are more (batch, head, 256-query) units than
+ * SMs, the units left over after the whole rounds are cut along the keys and spread over all SMs; their partial (O, m, l) go
+ * through this workspace and a merge kernel.  workspace may be NULL (or too small): the leftover units then run whole. */
+int64_t aria_attention_fwd_workspace_bytes(int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t out_hd, int32_t causal);
 /* Single-token decode against a KV cache (HBM-bound, split-KV): q element (b,h,:) at q + b*q_stride_b + h*q_stride_h
  * (128 contiguous bf16), cache [B,H,Tk_max,128], out [B, H*128].  workspace: B*H*splits*(128+2) floats.
  * key_mask [B, Tk] uint8 or NULL: 1 = key is masked OUT (padded batch: the HF 2-D attention_mask inverted). */

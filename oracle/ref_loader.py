@@ -12,7 +12,7 @@ transformers 5.5 (`aria/model/__init__.py` pulls in processors whose imports mov
   3. load the five model files by path.
 Two lines of the reference cannot execute on CPU and are shimmed *outside* the reference files:
   - moe_lm.py:264 `torch.histc` on int64 (no CPU kernel)  -> cast to float and back
-  - moe_lm.py:483 `torch.cuda.set_device(cpu tensor)`     -> no-op
+  - moe_lm.py:483 `torch.cuda.set_device(cpu tensor)`     -> no-op for CPU devices (also on a box that has GPUs)
 """
 import importlib.util
 import os
@@ -60,8 +60,20 @@ def load_reference():
 
         histc._aria_shim = True
         torch.histc = histc
-    if not torch.cuda.is_available():
-        torch.cuda.set_device = lambda *_a, **_k: None
+    if not getattr(torch.cuda.set_device, "_aria_shim", False):
+        _set_device = torch.cuda.set_device
+
+        def set_device(device):
+            # moe_lm.py:483 calls this with `input.device`; for a CPU tensor there is nothing to select (and torch raises)
+            if isinstance(device, torch.device) and device.type != "cuda":
+                return
+            if isinstance(device, str) and not device.startswith("cuda"):
+                return
+            if torch.cuda.is_available():
+                _set_device(device)
+
+        set_device._aria_shim = True
+        torch.cuda.set_device = set_device
 
     for name in ("aria", "aria.model"):
         if name not in sys.modules:

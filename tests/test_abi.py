@@ -123,7 +123,11 @@ def test_bench_gpu_leg_does_not_touch_oracle():
     body = ast.get_source_segment(src, fn)
     imports = re.findall(r"^\s*(?:from|import)\s+(\S+)", body, flags=re.M)
     assert not [m for m in imports if m.startswith("oracle")], imports
-    assert "CpuReference" in body  # the one allowed use: the cpu_baseline leg at N=1
+    assert "make_cpu_reference" in body  # the one allowed use: the cpu_baseline leg at N=1
+    # ... and the GPU workload classes (what run_aria times) never import oracle/ either
+    for cls in (n for n in tree.body if isinstance(n, ast.ClassDef) and n.name.startswith("Cfg")):
+        seg = ast.get_source_segment(src, cls)
+        assert not [m for m in re.findall(r"^\s*(?:from|import)\s+(\S+)", seg, flags=re.M) if m.startswith("oracle")], cls.name
 
 
 def test_top_level_model_helpers_match_the_reference_api():

@@ -46,4 +46,45 @@ def test_peaks_come_from_the_driver_file_or_the_documented_fallback():
 
 def test_workload_is_baseline_cfg2():
     b = _bench()
-    assert b.T_TOTAL == 768 and "cfg2" in b.WORKLOAD and b.METRIC == "Aria-25.3B bf16 prefill tokens/sec"
+    assert b.T_TOTAL == 768 and "cfg2" in b.WORKLOADS["cfg2"] and b.METRICS["cfg2"] == "Aria-25.3B bf16 prefill tokens/sec"
+    assert set(b.GPU_WORKLOADS) == {"cfg2", "cfg3", "cfg4", "cfg5"}
+
+
+def test_op_work_models_match_survey_8d():
+    """Algorithmic FLOPs / bytes the per-kernel table divides by: checked on the cfg-2 shapes."""
+    import torch
+    b = _bench()
+    meta = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device="meta")   # noqa: E731
+    # fc1 grouped GEMM + SwiGLU at 768 tokens: 6*768 rows x [64, 2560, 3328]
+    lab, fl, by = b.op_work("grouped_gemm", (meta(4608, 2560), meta(64, 2560, 3328), meta(65, dt=torch.int32)), {"swiglu": True})
+    assert "swiglu" in lab and fl == 2 * 4608 * 2560 * 3328
+    assert by == 2 * (64 * 2560 * 3328 + 4608 * 2560 + 4608 * 1664) == 1129447424          # the number VERDICT r1 recomputed
+    # ViT attention, one layer: 4 * 16 * 4900^2 * 72 FLOP
+    q = meta(1, 16, 4900, 128)
+    lab, fl, by = b.op_work("attention", (q, q, q, 4900, 4900, 0.1, False), {"out_hd": 72})
+    assert fl == 4 * 16 * 4900 * 4900 * 72 and "hd72" in lab
+    # causal LM attention: 5120 * T^2 per layer up to the diagonal term
+    q = meta(1, 20, 768, 128)
+    _, fl, _ = b.op_work("attention", (q, q, q, 768, 768, 0.1, True), {})
+    assert abs(fl / (5120 * 768 * 768) - 1) < 2e-3
+    _, fl, by = b.op_work("linear", (meta(768, 2560), meta(2560, 2560)), {})
+    assert fl == 2 * 768 * 2560 * 2560 and by == 2 * (768 * 2560 * 2 + 2560 * 2560)
+
+
+def test_kernel_table_picks_the_dominant_kernel_by_share():
+    b = _bench()
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    kt = b.KernelTable.__new__(b.KernelTable)
+    kt.events = [("attention[x]", 110.6e9, 1e6, Ev(0.0), Ev(0.2)), ("gemm[y]", 1e6, 1.1e9, Ev(0.0), Ev(0.15)),
+                 ("attention[x]", 110.6e9, 1e6, Ev(1.0), Ev(1.2))]
+    rows = kt.table(1, 1.0, {"hbm_gbs": 6484.6, "bf16_tflops": 1739.4, "bf16_tflops_sustained": 1480.4})
+    assert rows[0]["kernel"] == "attention[x]" and rows[0]["bound"] == "tensor" and abs(rows[0]["share"] - 0.4) < 1e-9
+    assert abs(rows[0]["achieved"] - 553.0) < 1.0 and abs(rows[0]["frac"] - 553.0 / 1480.4) < 1e-3
+    assert rows[1]["bound"] == "hbm" and abs(rows[1]["achieved"] - 1.1e9 / 0.15 / 1e6) < 1e-6
