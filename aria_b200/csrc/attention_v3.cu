@@ -27,8 +27,31 @@ namespace aria {
 
 constexpr int A3_BM = 128, A3_BN = 128;
 constexpr int A3_THREADS = 384;  // WG0: warp 0 TMA, warp 1 / 2 MMA issuers of tile 0 / 1, warp 3 TMEM owner; WG1 / WG2: softmax tile 0 / 1
+// ---- build-time switches (scripts/build_variant.sh; measurements in profiles/r02_attention_notes.txt)
+#ifndef ARIA_ATTN_PF16
+#define ARIA_ATTN_PF16 1    // P as packed fp16 straight out of ex2.approx.f16x2 (one MUFU op per two keys); 0: fp32 ex2 + bf16 pack
+#endif
 #ifndef ARIA_ATTN_POLY
-#define ARIA_ATTN_POLY 4   // of every 16 exponent pairs (32 keys), how many go through exp2_poly2 instead of MUFU (0..16)
+#define ARIA_ATTN_POLY 0    // (PF16 = 0 only) of every 16 exponent pairs, how many go through exp2_poly2 instead of MUFU (0..16)
+#endif
+#ifndef ARIA_ATTN_SEQ
+#define ARIA_ATTN_SEQ 0     // 1: the two softmax warpgroups take turns exponentiating (token passing; measured: no gain)
+#endif
+#ifndef ARIA_ATTN_ABLATE
+#define ARIA_ATTN_ABLATE 0  // measurement-only variants (WRONG results): bit0 no exp math, bit1 no LDTM of S, bit2 no PV MMAs,
+#endif                      // bit3 no QK MMAs, bit4 no STTM of P
+#ifndef ARIA_ATTN_TRACE
+#define ARIA_ATTN_TRACE 0   // measurement-only: per-role cycle accounting of CTA 0 written behind the workspace (scripts/trace_attn.py)
+#endif
+#if ARIA_ATTN_TRACE
+#define TRACE_DECL long long tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t0 = clock64(); const long long tr_start = tr_t0
+#define TRACE_MARK(slot) do { const long long tr_now = clock64(); tr_acc[slot] += tr_now - tr_t0; tr_t0 = tr_now; } while (0)
+#define TRACE_DUMP(base) do { if (blockIdx.x == 0 && p.partial) { for (int z = 0; z < 12; ++z) p.partial[3200000 + (base) + z] = static_cast<float>(tr_acc[z]); \
+                                p.partial[3200000 + (base) + 12] = static_cast<float>(clock64() - tr_start); } } while (0)
+#else
+#define TRACE_DECL
+#define TRACE_MARK(slot)
+#define TRACE_DUMP(base)
 #endif
 
 struct Attn3Params {
@@ -105,10 +128,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
   uint64_t* v_full = bars + 4 + STAGES;  // [STAGES]
   uint64_t* kv_empty = bars + 4 + 2 * STAGES;  // [STAGES], 2 arrivals (one per issuer)
   uint64_t* s_full = bars + 4 + 3 * STAGES;    // [2]
-  uint64_t* p_full = s_full + 2;               // [2 tiles][2 halves]
+  uint64_t* p_full = s_full + 2;               // [2 tiles][2 halves], 4 arrivals (one per softmax warp)
   uint64_t* o_full = p_full + 4;               // [2]
-  uint64_t* o_empty = o_full + 2;              // [2], 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* o_empty = o_full + 2;              // [2], 4 arrivals
+  uint64_t* seq = o_empty + 2;                 // [2], 4 arrivals: whose turn it is to exponentiate (ARIA_ATTN_SEQ)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seq + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -123,10 +147,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[2 * i], 128);
-      mbar_init(&p_full[2 * i + 1], 128);
+      // softmax -> issuer hand-offs: ONE arrival per warp (lane 0 after __syncwarp), not one per thread
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
+      mbar_init(&o_empty[i], 4);
+      mbar_init(&seq[i], 4);
     }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&k_full[i], 1);
@@ -162,6 +188,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
     if (warp == 0) {
       // =========================== TMA producer ===========================
       if (elect_one()) {
+        TRACE_DECL;
         uint32_t kv_it = 0;  // K/V blocks produced so far (ring position)
         WorkItem w;
         for (int i = 0; get_item(p, cta, i, w); ++i) {
@@ -169,6 +196,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
           const int q0 = w.q_pair * 2 * A3_BM;
           for (int t = 0; t < 2; ++t) {
             mbar_wait(&q_empty[t], (i & 1) ^ 1);
+            TRACE_MARK(0);
             mbar_arrive_expect_tx(&q_full[t], C::QK_TILE);
             tma_load_4d(sQ + t * C::QK_TILE, &tmQ0, &q_full[t], 0, q0 + t * A3_BM, h, b);
             tma_load_4d(sQ + t * C::QK_TILE + C::CH0, &tmQ1, &q_full[t], 64, q0 + t * A3_BM, h, b);
@@ -176,7 +204,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
           const int kv_end = max(tile_kv_end(w, 0), tile_kv_end(w, 1));
           for (int j = w.kv0; j < kv_end; ++j, ++kv_it) {
             const int s = kv_it % STAGES;
+            TRACE_MARK(2);
             mbar_wait(&kv_empty[s], ((kv_it / STAGES) & 1) ^ 1);
+            TRACE_MARK(1);
             uint8_t* dk = sK + s * C::QK_TILE;
             mbar_arrive_expect_tx(&k_full[s], C::QK_TILE);
             tma_load_4d(dk, &tmK0, &k_full[s], 0, j * A3_BN, h, b);
@@ -192,13 +222,15 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
             }
           }
         }
+        TRACE_MARK(2);
+        TRACE_DUMP(0);
       }
     } else if (warp <= 2) {
       // =========================== MMA issuer of tile t ===========================
       const int t = warp - 1;
       if (elect_one()) {
         constexpr uint32_t idesc_qk = make_idesc_bf16(A3_BM, A3_BN, false, false);
-        constexpr uint32_t idesc_pv = make_idesc_bf16(A3_BM, HD, false, true);
+        constexpr uint32_t idesc_pv = ARIA_ATTN_PF16 ? make_idesc_f16a_bf16b(A3_BM, HD, true) : make_idesc_bf16(A3_BM, HD, false, true);
         const uint32_t sQa = smem_u32(sQ) + t * C::QK_TILE, sKa = smem_u32(sK), sVa = smem_u32(sV);
         const uint64_t dQ0 = make_smem_desc_sw(sQa, 16, 1024, UMMA_SW128);
         const uint64_t dQ1 = W == 80 ? make_smem_desc_sw(sQa + C::CH0, 16, 256, UMMA_SW32) : make_smem_desc_sw(sQa + C::CH0, 16, 1024, UMMA_SW128);
@@ -214,24 +246,32 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         uint32_t blk = 0;     // blocks THIS tile has processed (phase of s_full / p_full)
         uint32_t done = 0;    // items in which this tile had work (phase of o_full / o_empty)
         WorkItem w;
+        TRACE_DECL;
         auto issue_qk = [&](uint32_t ring) {
           const uint32_t st = ring % STAGES;
+          TRACE_MARK(5);
           mbar_wait(&k_full[st], (ring / STAGES) & 1);
+          TRACE_MARK(0);
           tc_fence_after();
           const uint64_t dk0 = dK0 + st * (C::QK_TILE >> 4), dk1 = dK1 + st * (C::QK_TILE >> 4);
+          if (!(ARIA_ATTN_ABLATE & 8)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ0 + k * 2, dk0 + k * 2, idesc_qk, k ? 1u : 0u);
-          // second chunk: columns 64.. of the head (HD = 80: one more k-step, whichever way the chunk is staged)
+            for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ0 + k * 2, dk0 + k * 2, idesc_qk, k ? 1u : 0u);
+            // second chunk: columns 64.. of the head (HD = 80: one more k-step, whichever way the chunk is staged)
 #pragma unroll
-          for (int k = 0; k < (HD - 64) / 16; ++k) umma_bf16_ss(tS, dQ1 + k * 2, dk1 + k * 2, idesc_qk, 1u);
+            for (int k = 0; k < (HD - 64) / 16; ++k) umma_bf16_ss(tS, dQ1 + k * 2, dk1 + k * 2, idesc_qk, 1u);
+          }
           umma_commit_addr(s_full_a);
         };
         for (int i = 0; get_item(p, cta, i, w); ++i) {
           const int n_all = max(tile_kv_end(w, 0), tile_kv_end(w, 1)) - w.kv0;  // blocks the producer streams for this item
           const int n_t = tile_kv_end(w, t) - w.kv0;                             // blocks this tile contracts
           if (n_t > 0) {
+            TRACE_MARK(5);
             mbar_wait(&q_full[t], i & 1);
+            TRACE_MARK(1);
             mbar_wait(&o_empty[t], (done & 1) ^ 1);  // previous item's epilogue has drained S/P/O of this tile
+            TRACE_MARK(2);
             tc_fence_after();
             issue_qk(kv_it);
             ++done;
@@ -239,16 +279,20 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
           for (int j = 0; j < n_all; ++j) {
             const uint32_t ring = kv_it + j, st = ring % STAGES;
             if (j < n_t) {
+              TRACE_MARK(5);
               mbar_wait(&v_full[st], (ring / STAGES) & 1);
+              TRACE_MARK(3);
               const uint64_t dv = dV0 + st * (C::V_TILE >> 4);
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
+                TRACE_MARK(5);
                 mbar_wait_addr(p_full_a + c * 8, blk & 1);
+                TRACE_MARK(4);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                   const int k = c * 4 + kk;
-                  umma_bf16_ts(tO, tS + k * 8, dv + k * v_kadv, idesc_pv, (j | k) ? 1u : 0u);
+                  if (!(ARIA_ATTN_ABLATE & 4)) umma_bf16_ts(tO, tS + k * 8, dv + k * v_kadv, idesc_pv, (j | k) ? 1u : 0u);
                 }
               }
               ++blk;
@@ -270,6 +314,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
           }
           kv_it += n_all;
         }
+        TRACE_MARK(5);
+        TRACE_DUMP(16 + 16 * t);
       }
     }
   } else {
@@ -282,8 +328,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
     const uint32_t tS = tmem_base + t * 128 + lane_addr;
     const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
     const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
-    uint32_t blk = 0, done = 0;
+    uint32_t blk = 0, done = 0, rounds = 0;
     WorkItem w;
+    TRACE_DECL;
     for (int i = 0; get_item(p, cta, i, w); ++i) {
       const int b = w.bh / p.H, h = w.bh % p.H;
       const int q0 = w.q_pair * 2 * A3_BM + t * A3_BM;
@@ -291,94 +338,144 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       const bool row_ok = q < p.Tq;
       const int qpos = pos_off + q;
       const int kv_end = tile_kv_end(w, t);
+      const int kv_end_all = ARIA_ATTN_SEQ ? max(tile_kv_end(w, 0), tile_kv_end(w, 1)) : kv_end;
       const uint8_t* km = p.key_mask ? p.key_mask + static_cast<int64_t>(b) * p.Tk : nullptr;
       float m_ref = -INFINITY, l = 0.f;
-      if (kv_end <= w.kv0) continue;  // tile without work in this item (the issuer skips it too)
 
-      for (int j = w.kv0; j < kv_end; ++j, ++blk) {
-        mbar_wait(&s_full[t], blk & 1);
-        tc_fence_after();
-        const int k0 = j * A3_BN;
-        const bool need_mask = (k0 + A3_BN > p.Tk) || (CAUSAL && (k0 + A3_BN - 1 > pos_off + q0)) || km != nullptr;
+      // (ARIA_ATTN_SEQ: the exp phase is a token passed between the two softmax warpgroups — tile 0 block j, tile 1 block j,
+      // tile 0 block j+1, ... — to force the tiles out of phase; a tile without work in a round still takes and passes it.)
+      for (int j = w.kv0; j < kv_end_all; ++j, ++rounds) {
+        const bool active = j < kv_end;
         uint32_t sr[4][32];
+        float mx = -INFINITY;
+        const int k0 = j * A3_BN;
+        bool need_mask = false;
+        if (active) {
+          TRACE_MARK(7);
+          mbar_wait(&s_full[t], blk & 1);
+          TRACE_MARK(0);
+          ++blk;
+          tc_fence_after();
+          need_mask = (k0 + A3_BN > p.Tk) || (CAUSAL && (k0 + A3_BN - 1 > pos_off + q0)) || km != nullptr;
+          if (!(ARIA_ATTN_ABLATE & 2)) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sr[c]);
-        tmem_ld_wait();
-        if (need_mask) {  // rare path (diagonal / tail / padded keys): -inf on dead keys
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, sr[c]);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int e = 0; e < 32; ++e) sr[c][e] = __float_as_uint(static_cast<float>((e * 7 + c + lane) & 15) * 0.25f);
+          }
+          if (need_mask) {  // rare path (diagonal / tail / padded keys): -inf on dead keys
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int kc = k0 + c * 32 + e;
+                const bool dead = kc >= p.Tk || (CAUSAL && kc > qpos) || (km && kc < p.Tk && km[kc]);
+                if (dead) sr[c][e] = 0xff800000u;
+              }
+            }
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmax3(mx0, __uint_as_float(sr[0][e]), __uint_as_float(sr[0][e + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(sr[1][e]), __uint_as_float(sr[1][e + 1]));
+            mx2 = fmax3(mx2, __uint_as_float(sr[2][e]), __uint_as_float(sr[2][e + 1]));
+            mx3 = fmax3(mx3, __uint_as_float(sr[3][e]), __uint_as_float(sr[3][e + 1]));
+          }
+          mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        }
+        TRACE_MARK(1);
+        if (ARIA_ATTN_SEQ) mbar_wait(&seq[t], t == 0 ? ((rounds & 1) ^ 1) : (rounds & 1));   // my turn
+        TRACE_MARK(2);
+        if (active) {
+          const float m_new = fmaxf(m_ref, mx * p.scale_log2);
+          const bool want = (m_new - m_ref > 8.0f) || (m_ref == -INFINITY && m_new > -INFINITY);
+          if (__any_sync(0xffffffffu, want)) {
+            const float f = (m_ref == -INFINITY) ? 0.f : fast_ex2(m_ref - m_new);
+            l *= f;
+            m_ref = m_new;
+            if (j > w.kv0) {
+#pragma unroll 1
+              for (int c = 0; c < HD; c += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(tO + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+                tmem_st_32x16(tO + c, v);
+              }
+            }
+          }
+          const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+          const uint64_t negm2 = pack_f2(neg_m, neg_m);
+          uint64_t lacc0 = 0ull, lacc1 = 0ull;  // packed (0.f, 0.f)
+          float lh = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+            if (ARIA_ATTN_PF16) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int kc = k0 + c * 32 + e;
-              const bool dead = kc >= p.Tk || (CAUSAL && kc > qpos) || (km && kc < p.Tk && km[kc]);
-              if (dead) sr[c][e] = 0xff800000u;
-            }
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+              for (int e = 0; e < 16; ++e) {  // pair e = keys 2e, 2e+1 of this 32-key chunk: ONE MUFU op for both
+                float x0, x1;
+                unpack_f2(fma2(pack_u2(sr[c][2 * e], sr[c][2 * e + 1]), scale2, negm2), x0, x1);
+                pk[e] = (ARIA_ATTN_ABLATE & 1) ? __float_as_uint(x0) : ex2_f16x2(x0, x1);
+              }
+              // row sum of the chunk: pairwise tree in fp16 (32 values, each <= 2^8), then fp32
+              uint32_t t8[8], t4[4];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          mx0 = fmax3(mx0, __uint_as_float(sr[0][e]), __uint_as_float(sr[0][e + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sr[1][e]), __uint_as_float(sr[1][e + 1]));
-          mx2 = fmax3(mx2, __uint_as_float(sr[2][e]), __uint_as_float(sr[2][e + 1]));
-          mx3 = fmax3(mx3, __uint_as_float(sr[3][e]), __uint_as_float(sr[3][e + 1]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        const float m_new = fmaxf(m_ref, mx * p.scale_log2);
-        const bool want = (m_new - m_ref > 8.0f) || (m_ref == -INFINITY && m_new > -INFINITY);
-        if (__any_sync(0xffffffffu, want)) {
-          const float f = (m_ref == -INFINITY) ? 0.f : fast_ex2(m_ref - m_new);
-          l *= f;
-          m_ref = m_new;
-          if (j > w.kv0) {
-#pragma unroll 1
-            for (int c = 0; c < HD; c += 16) {
-              uint32_t v[16];
-              tmem_ld_32x16(tO + c, v);
-              tmem_ld_wait();
+              for (int e = 0; e < 8; ++e) t8[e] = hadd2(pk[2 * e], pk[2 * e + 1]);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
-              tmem_st_32x16(tO + c, v);
-            }
-          }
-        }
-        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-        const uint64_t negm2 = pack_f2(neg_m, neg_m);
-        uint64_t lacc0 = 0ull, lacc1 = 0ull;  // packed (0.f, 0.f)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {  // pair e = keys 2e, 2e+1 of this 32-key chunk
-            const uint64_t x = fma2(pack_u2(sr[c][2 * e], sr[c][2 * e + 1]), scale2, negm2);
-            uint64_t pe;
-            if (e < ARIA_ATTN_POLY) {
-              pe = exp2_poly2(x);
+              for (int e = 0; e < 4; ++e) t4[e] = hadd2(t8[2 * e], t8[2 * e + 1]);
+              lh += half2_sum_f32(hadd2(hadd2(t4[0], t4[1]), hadd2(t4[2], t4[3])));
             } else {
-              float x0, x1;
-              unpack_f2(x, x0, x1);
-              pe = pack_f2(fast_ex2(x0), fast_ex2(x1));
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {  // pair e = keys 2e, 2e+1 of this 32-key chunk
+                const uint64_t x = fma2(pack_u2(sr[c][2 * e], sr[c][2 * e + 1]), scale2, negm2);
+                uint64_t pe;
+                if (ARIA_ATTN_ABLATE & 1) {
+                  pe = x;
+                } else if (e < ARIA_ATTN_POLY) {
+                  pe = need_mask ? exp2_poly2<true>(x) : exp2_poly2<false>(x);
+                } else {
+                  float x0, x1;
+                  unpack_f2(x, x0, x1);
+                  pe = pack_f2(fast_ex2(x0), fast_ex2(x1));
+                }
+                if (e & 1) lacc1 = add2(lacc1, pe); else lacc0 = add2(lacc0, pe);
+                float p0, p1;
+                unpack_f2(pe, p0, p1);
+                pk[e] = pack_bf16(p0, p1);
+              }
             }
-            if (e & 1) lacc1 = add2(lacc1, pe); else lacc0 = add2(lacc0, pe);
-            float p0, p1;
-            unpack_f2(pe, p0, p1);
-            pk[e] = pack_bf16(p0, p1);
+            // P chunk (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16): S is already in registers
+            if (!(ARIA_ATTN_ABLATE & 16)) tmem_st_32x16(tS + c * 16, pk);
+            if (c & 1) {  // 64 keys complete -> hand them to the PV MMA
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&p_full[2 * t + (c >> 1)]);
+            }
           }
-          // P chunk (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16): S is already in registers
-          tmem_st_32x16(tS + c * 16, pk);
-          if (c & 1) {  // 64 keys complete -> hand them to the PV MMA
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[2 * t + (c >> 1)]);
-          }
+          TRACE_MARK(3);
+          if (ARIA_ATTN_SEQ && lane == 0) mbar_arrive(&seq[1 - t]);   // pass the token (the p_full arrival synchronised the warp)
+          float la, lb;
+          unpack_f2(add2(lacc0, lacc1), la, lb);
+          l += la + lb + lh;
+        } else if (ARIA_ATTN_SEQ) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&seq[1 - t]);
         }
-        float la, lb;
-        unpack_f2(add2(lacc0, lacc1), la, lb);
-        l += la + lb;
       }
+      if (kv_end <= w.kv0) continue;  // tile without work in this item (its issuer skipped it too)
 
       // ---- epilogue of the item: O (TMEM, fp32, relative to m_ref) -> out (normalised bf16) or -> partial slot
+      TRACE_MARK(7);
       mbar_wait(&o_full[t], done & 1);
+      TRACE_MARK(4);
       ++done;
       tc_fence_after();
       if (w.slot < 0) {
@@ -416,8 +513,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         prow[HD + 1] = l;
       }
       tc_fence_before();
-      mbar_arrive(&o_empty[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[t]);
+      TRACE_MARK(5);
     }
+    if (r == 0) TRACE_DUMP(48 + 16 * t);
   }
   tc_fence_before();
   __syncthreads();
@@ -551,6 +651,14 @@ extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, v
       if (p.split > p.n_kv_all) p.split = p.n_kv_all;
       if (p.split < 1) p.split = 1;
     }
+  } else if (!causal && persist && can_split && units * 2 <= sms && p.n_kv_all >= 4) {
+    // fewer units than SMs (the projector's cross-attention: 16 heads x 256 queries against 4900 keys): every unit is cut
+    // along the keys so that all SMs work, pieces merged as above
+    p.full_rounds = 0;
+    p.leftover = static_cast<int>(units);
+    p.split = sms / p.leftover;
+    if (p.split > p.n_kv_all / 2) p.split = p.n_kv_all / 2;
+    p.n_cta = p.leftover * p.split;
   } else {
     p.n_cta = static_cast<int>(units);
     p.full_rounds = 1;

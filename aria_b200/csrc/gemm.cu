@@ -195,7 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = r_in_grp < rows;
       const int64_t grow = static_cast<int64_t>(row0) + r_in_grp;
 
-      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2);
+      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2, grp, r_in_grp);
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -261,6 +261,9 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     else ARIA_CHECK_ARG(d->num_groups == 1);
   }
   if (d->num_groups > 1) ARIA_CHECK_ARG(d->group_offsets != nullptr);
+  if (d->group_counts) ARIA_CHECK_ARG(d->group_offsets != nullptr);
+  if (d->out_group_base) ARIA_CHECK_ARG(d->out_group_row0 != nullptr && d->epilogue == ARIA_EPI_LINEAR && d->group_offsets != nullptr);
+  ARIA_CHECK_ARG(d->a_rows == 0 || d->a_rows >= d->m);
 
   GemmParams p{};
   p.M = static_cast<int>(d->m);
@@ -268,6 +271,9 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   p.K = static_cast<int>(d->k);
   p.num_groups = d->num_groups;
   p.group_offsets = d->group_offsets;
+  p.group_counts = d->group_counts;
+  p.out_group_base = static_cast<const uint64_t*>(d->out_group_base);
+  p.out_group_row0 = d->out_group_row0;
   p.group_mod = d->group_mod;
   p.b_group_rows = b_gnk ? static_cast<int>(d->n) : 0;
   p.n_seg = swiglu ? 1 : d->n_seg;
@@ -365,7 +371,9 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   }
 
   CUtensorMap tmA, tmB[3];
-  int rc = make_tmap_2d(&tmA, d->a, d->k, d->m, d->lda * 2, BK, AM);
+  // a_rows: rows of the A buffer when groups live in fixed-capacity regions (m is then the EXPECTED row count that the
+  // kernel-selection heuristics above use; the tensor map must cover the whole buffer)
+  int rc = make_tmap_2d(&tmA, d->a, d->k, d->a_rows > 0 ? d->a_rows : d->m, d->lda * 2, BK, AM);
   if (rc) return rc;
   if (b_mn) {
     const uint64_t ncols = swiglu ? 2 * d->n : d->n;

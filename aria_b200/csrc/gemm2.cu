@@ -188,7 +188,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int r_in_grp = m_idx * BM2 + r_in_tile;
       const bool row_ok = r_in_grp < rows;
       const int64_t grow = static_cast<int64_t>(row0) + r_in_grp;
-      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2);
+      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2, grp, r_in_grp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tempty0 + as * 8);

@@ -29,6 +29,9 @@ struct GemmParams {
   int M, N, K;  // N = output columns per segment
   int num_groups;
   const int32_t* group_offsets;
+  const int32_t* group_counts;     // non-NULL: group g = rows [group_offsets[g], + group_counts[g]) (fixed-capacity regions)
+  const uint64_t* out_group_base;  // non-NULL (LINEAR): rows of group g are stored at out_group_base[g] + (out_group_row0[g] + r)*ldo
+  const int32_t* out_group_row0;   //   — e.g. straight into the source rank's combine buffer over NVLink (expert parallelism)
   int b_group_rows;  // K-major grouped weights [G, N, K]: B row of (group g, column c) is g*b_group_rows + c (0: dense)
   int group_mod;  // weight block of group g is g % group_mod (0: identity) — expert-parallel (src rank, expert) groups
   int n_seg;
@@ -51,11 +54,13 @@ struct GemmParams {
 // then n-tile, with the m-tile innermost so that CTAs running concurrently share the same weight tile.
 struct TileSched {
   const int32_t* offs;
+  const int32_t* cnts;
   int G, n_tiles, M;
   int g, mt_prefix, g_row0, g_rows, g_mt, bm;
   __device__ void init(const GemmParams& p, int n_tiles_, int bm_ = BM) {
     bm = bm_;
     offs = p.group_offsets;
+    cnts = p.group_counts;
     G = p.num_groups;
     n_tiles = n_tiles_;
     M = p.M;
@@ -69,7 +74,7 @@ struct TileSched {
     if (gi >= G) return false;
     if (offs) {
       g_row0 = offs[gi];
-      g_rows = offs[gi + 1] - g_row0;
+      g_rows = cnts ? cnts[gi] : offs[gi + 1] - g_row0;
     } else {
       g_row0 = 0;
       g_rows = M;
@@ -128,7 +133,7 @@ ARIA_DEVICE float act_apply(float x, int act) {
 // quadrant split the columns, so 8 epilogue warps drain one accumulator in half the time of 4.
 template <int BN, int EPI>
 ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const int n_out_total, const int n_idx,
-                               const int64_t grow, const bool row_ok, const int half) {
+                               const int64_t grow, const bool row_ok, const int half, const int grp = 0, const int r_in_grp = 0) {
   constexpr int OUT_BN = (EPI == ARIA_EPI_SWIGLU) ? BN / 2 : BN;
   if constexpr (EPI == ARIA_EPI_SWIGLU) {
     // out[:, n] = bf16( bf16(silu(bf16(gate))) * bf16(up) )  — rounding points of moe_lm.py:505-507
@@ -163,6 +168,8 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
     const int seg = col0 / p.N;  // bias is per segment; out is [m, n_seg*n]
     const __nv_bfloat16* bias = p.bias[seg];
     __nv_bfloat16* orow = p.out[0] + grow * p.ldo + col0;
+    if (p.out_group_base)  // per-group destination (possibly a peer GPU's memory: the stores then travel over NVLink)
+      orow = reinterpret_cast<__nv_bfloat16*>(p.out_group_base[grp]) + static_cast<int64_t>(p.out_group_row0[grp] + r_in_grp) * p.ldo + col0;
     const __nv_bfloat16* rrow = p.residual ? p.residual + grow * p.ldr + col0 : nullptr;
     constexpr int NCH = BN / 32;
     const int cb = (half * NCH / 2) * 32, ce = half ? BN : (NCH / 2) * 32;

@@ -308,6 +308,16 @@ ARIA_DEVICE uint64_t make_smem_desc_sw(uint32_t smem_addr, uint32_t lbo_bytes, u
   d |= static_cast<uint64_t>(swizzle) << 61;
   return d;
 }
+// kind::f16 instruction descriptor with A in fp16 (from TMEM) and B in bf16 (shared memory), fp32 accumulation: the
+// attention PV product with P produced directly as packed halves by ex2.approx.f16x2.
+__host__ __device__ constexpr uint32_t make_idesc_f16a_bf16b(int M, int N, bool b_mn_major) {
+  return (1u << 4)                       // D format: F32
+         | (0u << 7)                     // A format: F16
+         | (1u << 10)                    // B format: BF16
+         | ((b_mn_major ? 1u : 0u) << 16)
+         | (static_cast<uint32_t>(N >> 3) << 17)
+         | (static_cast<uint32_t>(M >> 4) << 24);
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                       // D format: F32
@@ -356,6 +366,25 @@ ARIA_DEVICE uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// two exponentials per MUFU op: x0, x1 (fp32) -> packed halves {2^x1 : 2^x0} (lo = x0).  fp16 carries 11 significant bits, so
+// the rounding of x costs <= 2^-12 |x| ln 2 relative error in 2^x (0.27 % at x = -16, 0.02 % at x = -1) and the result has 3 more
+// bits than the bf16 P the reference-style path multiplies with.
+ARIA_DEVICE uint32_t ex2_f16x2(float x0, float x1) {
+  uint32_t h, r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+ARIA_DEVICE uint32_t hadd2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+ARIA_DEVICE float half2_sum_f32(uint32_t h) {
+  float lo, hi;
+  asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n" : "=f"(lo), "=f"(hi) : "r"(h));
+  return lo + hi;
+}
 ARIA_DEVICE float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -365,17 +394,16 @@ ARIA_DEVICE float fmax3(float a, float b, float c) {
 // degree-3 minimax polynomial on the fraction (max rel. error ~9e-5, far below the bf16 rounding of P that follows) — the
 // FlashAttention-4 way of taking exponentials off the 16-per-clock MUFU unit.  x must be <= 0-ish (no overflow handling);
 // x < -125 (incl. -inf of masked keys) is clamped: the result is then ~2^-125, i.e. zero for every purpose here.
+template <bool CLAMP>
 ARIA_DEVICE uint64_t exp2_poly2(uint64_t x) {
-  float x0, x1;
-  unpack_f2(x, x0, x1);
-  x = pack_f2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-  const uint64_t magic = pack_f2(12582912.f, 12582912.f);       // 1.5 * 2^23: floor(x) lands in the low mantissa bits
-  const uint64_t r = add2_rm(x, magic);
-  const uint64_t fl = add2(r, pack_f2(-12582912.f, -12582912.f));  // floor(x) as a float (exact)
-  float f0, f1, g0, g1;
-  unpack_f2(x, f0, f1);
-  unpack_f2(fl, g0, g1);
-  const uint64_t fr = pack_f2(f0 - g0, f1 - g1);                 // fraction in [0, 1)
+  if (CLAMP) {  // only needed where a key can be masked to -inf
+    float x0, x1;
+    unpack_f2(x, x0, x1);
+    x = pack_f2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  }
+  const uint64_t r = add2_rm(x, pack_f2(12582912.f, 12582912.f));     // 1.5 * 2^23: floor(x) lands in the low mantissa bits
+  const uint64_t fl = add2(r, pack_f2(-12582912.f, -12582912.f));     // floor(x) as a float (exact)
+  const uint64_t fr = fma2(fl, pack_f2(-1.f, -1.f), x);               // fraction in [0, 1)
   uint64_t p = fma2(fr, pack_f2(0.077119089663028717f, 0.077119089663028717f), pack_f2(0.227564394474029541f, 0.227564394474029541f));
   p = fma2(p, fr, pack_f2(0.695146143436431885f, 0.695146143436431885f));
   p = fma2(p, fr, pack_f2(1.0f, 1.0f));

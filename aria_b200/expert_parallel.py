@@ -85,6 +85,8 @@ class ExpertParallelMoE:
         return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if isinstance(self.transport, FusedPeerTransport):
+            return _ep_forward_fused(self, x)
         if self.transport is not None:
             return _ep_forward_p2p(self, x)
         shape = x.shape
@@ -158,6 +160,87 @@ class PeerTransport:
             L.check(L.load().aria_peer_barrier(C.c_void_p(self.p_flags.data_ptr()), self.rank, self.W,
                                                C.c_void_p(self.epoch.data_ptr()),
                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "peer_barrier")
+
+
+class FusedPeerTransport:
+    """Round-2 exchange (csrc/ep.cu "Fused exchange"): fixed-capacity receive regions, the dispatch fused into the permute
+    kernel, the return path fused into the fc2 GEMM epilogue, two device-side barriers per layer, no host sync, CUDA-graph
+    friendly.  Arena of every rank (mapped by all peers):
+
+        meta_counts [W*E_loc] int32 | meta_row0 [W*E_loc] int32 | flags [W] int32
+        | recv_x [W*E_loc][cap][d] bf16 (region (s, el) = rows rank s routed to my expert el) | ret_y [T_max*k][d] bf16
+
+    cap = T_max rounded up to 16 (+16 for the training layout's alignment pads): a token picks an expert at most once."""
+
+    def __init__(self, T_max: int, hidden: int, inter: int, num_experts: int, topk: int, device, group=None):
+        from .peer import PeerArena
+        self.group = group
+        self.W = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.E, self.k, self.d = num_experts, topk, hidden
+        self.E_loc = num_experts // self.W
+        self.G = self.W * self.E_loc
+        self.cap = (T_max + 15) // 16 * 16 + 16
+        self.ret_rows = T_max * topk + num_experts * 15
+        al = lambda n: (n + 1023) // 1024 * 1024
+        self.off_counts = 0
+        self.off_row0 = al(self.G * 4)
+        self.off_flags = self.off_row0 + al(self.G * 4)
+        self.off_recv = self.off_flags + al(self.W * 4)
+        self.off_ret = self.off_recv + al(self.G * self.cap * hidden * 2)
+        total = self.off_ret + al(self.ret_rows * hidden * 2)
+        self.arena = PeerArena(total, device, group)
+        dev = torch.device(device)
+        mk = lambda off: torch.tensor([self.arena.ptr(r, off) for r in range(self.W)], dtype=torch.int64, device=dev)
+        self.p_counts, self.p_row0, self.p_flags = mk(self.off_counts), mk(self.off_row0), mk(self.off_flags)
+        self.p_recv, self.p_ret = mk(self.off_recv), mk(self.off_ret)
+        self.meta_counts = self.arena.local_view(self.off_counts, (self.G,), torch.int32)
+        self.meta_row0 = self.arena.local_view(self.off_row0, (self.G,), torch.int32)
+        self.recv_x = self.arena.local_view(self.off_recv, (self.G * self.cap, hidden), torch.bfloat16)
+        self.ret_y = self.arena.local_view(self.off_ret, (self.ret_rows, hidden), torch.bfloat16)
+        self.starts = (torch.arange(self.G, dtype=torch.int32) * self.cap).to(dev)
+        # group g = (source rank g // E_loc, local expert): its outputs go back into rank s's ret_y
+        self.out_base = self.p_ret.repeat_interleave(self.E_loc).contiguous()
+        self.h_buf = torch.empty((self.G * self.cap, inter), dtype=torch.bfloat16, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.device = dev
+
+    barrier = PeerTransport.barrier
+
+
+def _ep_forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+    """ExpertParallelMoE.forward on the fused exchange: 2 barriers + 0 copy kernels on top of the single-GPU launch sequence."""
+    import ctypes as C
+    from . import _lib as L
+    from . import ops
+    tr = self.transport
+    lib = L.load()
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1]).contiguous()
+    T = x2.shape[0]
+    assert T <= tr.cap - 16 and T * self.k <= tr.ret_rows, "FusedPeerTransport was sized for fewer tokens"
+    stream = C.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    from .moe_lm import join_side, shared_expert_overlapped
+    # the local shared expert runs as a parallel branch (side stream) while rows are in flight and experts compute
+    forked = shared_expert_overlapped(
+        lambda: ops.linear(ops.linear_swiglu(x2, self.w["shared_experts.gate_proj.weight"],
+                                             self.w["shared_experts.up_proj.weight"]), self.w["shared_experts.down_proj.weight"]), x2)
+    scores, idx, counts, _ = ops.router_topk(x2, self.w["router.weight"], self.k)
+    offsets, dest, src = ops.build_permutation(idx, counts)
+    with torch.cuda.device(x2.device):
+        # fused permute + dispatch over NVLink, and my per-block (count, first sorted row) into the owners' meta arrays
+        L.check(lib.aria_ep_dispatch(vp(x2), vp(src), vp(offsets), vp(tr.p_recv), vp(tr.p_counts), vp(tr.p_row0), tr.rank, tr.W,
+                                     tr.E, tr.cap, tr.d, T * self.k, stream), "ep_dispatch")
+    tr.barrier()
+    ops.grouped_gemm_regions(tr.recv_x, self.w["experts.fc1.weight"], tr.starts, tr.meta_counts, T * self.k, swiglu=True,
+                             group_mod=tr.E_loc, out=tr.h_buf)
+    # fc2: every output row is stored by the GEMM epilogue straight into its SOURCE rank's combine buffer (the return all-to-all)
+    ops.grouped_gemm_regions(tr.h_buf, self.w["experts.fc2.weight"], tr.starts, tr.meta_counts, T * self.k, group_mod=tr.E_loc,
+                             out_group_base=tr.out_base, out_group_row0=tr.meta_row0, ldo=tr.d)
+    tr.barrier()
+    shared = join_side(forked, x2)
+    return ops.unpermute_combine(tr.ret_y, dest, scores, shared).view(shape)
 
 
 def _ep_forward_p2p(self, x: torch.Tensor) -> torch.Tensor:

@@ -39,13 +39,15 @@ def _moe_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
     cfg = getattr(self.router, "config", None) or self.config
     shape = hidden_states.shape
     x = hidden_states.reshape(-1, shape[-1]).contiguous()
+    se = self.shared_experts
+    forked = _m.shared_expert_overlapped(
+        lambda: ops.linear(ops.linear_swiglu(x, se.gate_proj.weight, se.up_proj.weight), se.down_proj.weight), x)
     scores, idx, counts, _ = ops.router_topk(x, self.router.weight, cfg.moe_topk)
     offsets, dest, src = ops.build_permutation(idx, counts)
     permuted = ops.permute_rows(x, src)
     h = ops.grouped_gemm(permuted, self.experts.fc1.weight, offsets, swiglu=True)
     y = ops.grouped_gemm(h, self.experts.fc2.weight, offsets)
-    se = self.shared_experts
-    shared = ops.linear(ops.linear_swiglu(x, se.gate_proj.weight, se.up_proj.weight), se.down_proj.weight)
+    shared = _m.join_side(forked, x)
     return ops.unpermute_combine(y, dest, scores, shared).view(shape)
 
 

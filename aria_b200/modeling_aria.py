@@ -94,12 +94,13 @@ class AriaForConditionalGeneration(nn.Module):
     def enable_expert_parallel(self, max_tokens: int, group=None):
         """Shard the routed experts of every MoE layer over the ranks of `group` (rank r serves experts
         [r*E/W, (r+1)*E/W), a dim-0 view of the HF weights) and exchange token rows over NVLink peer memory
-        (aria_b200.expert_parallel.PeerTransport).  Every rank must then call forward() in lock-step with its own tokens."""
+        (aria_b200.expert_parallel.FusedPeerTransport: dispatch fused into the permute kernel, return path fused into the fc2
+        GEMM epilogue).  Every rank must then call forward() in lock-step with its own tokens."""
         import torch.distributed as dist
-        from .expert_parallel import ExpertParallelMoE, PeerTransport
+        from .expert_parallel import ExpertParallelMoE, FusedPeerTransport
         t = self.config.text_config
         W, r = dist.get_world_size(group), dist.get_rank(group)
-        tr = PeerTransport(max_tokens, t.hidden_size, t.moe_num_experts, t.moe_topk, self.device, group)
+        tr = FusedPeerTransport(max_tokens, t.hidden_size, t.moe_intermediate_size, t.moe_num_experts, t.moe_topk, self.device, group)
         lo, hi = r * t.moe_num_experts // W, (r + 1) * t.moe_num_experts // W
         for layer in self.language_model.model.layers:
             m = layer.mlp

@@ -215,6 +215,38 @@ class SharedExpertMLP(nn.Module):
         return ops.linear(h, self.down_proj.weight)
 
 
+_SIDE_STREAMS = {}
+
+
+def shared_expert_overlapped(fn, like: torch.Tensor):
+    """Run `fn()` (the shared-expert branch, moe_lm.py:575: independent of the routed branch until the final add) on a side
+    stream of `like`'s device, forked from / joined to the current stream — under CUDA-graph capture this becomes a parallel
+    branch of the graph.  At prefill sizes the branch is two latency-bound weight-streaming GEMMs that otherwise sit
+    serialised between HBM-saturating expert GEMMs.  ARIA_MOE_SIDE_STREAM=0 runs it in line."""
+    import os
+    if os.environ.get("ARIA_MOE_SIDE_STREAM", "1") == "0" or not like.is_cuda:
+        return fn()
+    dev = like.device
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    out.record_stream(cur)     # allocated on the side stream, consumed on the current one
+    return out, side
+
+
+def join_side(forked, like: torch.Tensor):
+    """Second half of `shared_expert_overlapped`: make the current stream wait for the side branch; returns its result."""
+    if isinstance(forked, tuple):
+        out, side = forked
+        torch.cuda.current_stream(like.device).wait_stream(side)
+        return out
+    return forked
+
+
 class MoELayer(nn.Module):
     """moe_lm.py:528-577.  forward(hidden_states [B,T,d]) -> [B,T,d]."""
 
@@ -229,10 +261,11 @@ class MoELayer(nn.Module):
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if self.expert_parallel is not None:
             return self.expert_parallel(hidden_states)
+        forked = shared_expert_overlapped(lambda: self.shared_experts(hidden_states), hidden_states)
         scores, indices, tokens_per_expert = self.router(hidden_states)
         permuted_tokens = self.token_dispatcher.token_permutation(hidden_states, indices, tokens_per_expert)
         expert_output = self.experts(permuted_tokens, self.token_dispatcher.expert_offsets)
-        shared_expert_output = self.shared_experts(hidden_states)
+        shared_expert_output = join_side(forked, hidden_states)
         # unpermute + score-weighted sum + `output += shared_expert_output` (moe_lm.py:573-576) in one kernel
         return self.token_dispatcher.token_unpermutation(expert_output, scores, shared_expert_output)
 

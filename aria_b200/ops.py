@@ -133,6 +133,46 @@ def grouped_gemm(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, swiglu
     return out
 
 
+def grouped_gemm_regions(a_buf: torch.Tensor, b: torch.Tensor, starts: torch.Tensor, counts: torch.Tensor, rows_hint: int,
+                         swiglu: bool = False, group_mod: int = 0, out: Optional[torch.Tensor] = None,
+                         out_group_base: Optional[torch.Tensor] = None, out_group_row0: Optional[torch.Tensor] = None,
+                         ldo: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Grouped GEMM over FIXED-CAPACITY row regions (expert parallelism, csrc/ep.cu): group g = rows
+    [starts[g], starts[g] + counts[g]) of `a_buf`, multiplied by weight block g % group_mod.  `counts` may be written by peer
+    GPUs (it is read on the device at launch).  rows_hint = expected total rows (tile-shape heuristics only).
+    With out_group_base / out_group_row0 the rows of group g are stored at (bf16*)out_group_base[g] + (out_group_row0[g] + r)*ldo
+    — e.g. straight into the source rank's combine buffer over NVLink — and nothing is returned."""
+    _chk(a_buf), _chk(b), _chk(starts, torch.int32, align=4), _chk(counts, torch.int32, align=4)
+    cap_rows, K = a_buf.shape
+    E, Kb, Nb = b.shape
+    G = starts.numel()
+    assert Kb == K and counts.numel() == G and (G == E if not group_mod else (group_mod == E and G % E == 0))
+    N = Nb // 2 if swiglu else Nb
+    d = L.GemmDesc()
+    d.a, d.lda, d.m, d.n, d.k = a_buf.data_ptr(), K, max(1, min(rows_hint, cap_rows)), N, K
+    d.a_rows = cap_rows
+    d.b[0] = b.data_ptr()
+    d.n_seg, d.b_layout, d.num_groups = 1, L.B_GKN, G
+    d.group_mod = group_mod
+    d.group_offsets, d.group_counts = starts.data_ptr(), counts.data_ptr()
+    d.epilogue = L.EPI_SWIGLU if swiglu else L.EPI_LINEAR
+    if out_group_base is not None:
+        assert not swiglu and out_group_row0 is not None and ldo is not None
+        _chk(out_group_base, torch.int64, align=8), _chk(out_group_row0, torch.int32, align=4)
+        d.out_group_base, d.out_group_row0 = out_group_base.data_ptr(), out_group_row0.data_ptr()
+        d.out[0], d.ldo = a_buf.data_ptr(), ldo      # out[0] is never dereferenced on this path (must be non-NULL)
+        ret = None
+    else:
+        if out is None:
+            out = torch.empty((cap_rows, N), dtype=bf16, device=a_buf.device)
+        _chk(out)
+        assert out.shape == (cap_rows, N)
+        d.out[0], d.ldo = out.data_ptr(), N
+        ret = out
+    _run_gemm(d, a_buf, "grouped_gemm")
+    return ret
+
+
 def grouped_gemm_nt(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, group_mod: int = 0,
                     residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Data-gradient of the grouped GEMM: out[rows of e] = a[rows of e] @ b[e].T (+ residual) with b [E, N_out, K]

@@ -79,6 +79,17 @@ typedef struct aria_gemm_desc {
   const int32_t* position_ids; /* [m] or NULL (then position = pos0 + token)                              */
   /* debug overrides of the UMMA shared-memory descriptor fields (0 = default); bring-up only            */
   int32_t dbg_lbo, dbg_sbo, dbg_kadv;
+  /* Expert parallelism over NVLink peer memory (fused compute + collective):
+   *   group_counts  non-NULL: group g = rows [group_offsets[g], group_offsets[g] + group_counts[g]) — fixed-capacity
+   *                 regions a peer GPU fills without knowing the other senders' counts; a_rows = rows of the A buffer
+   *                 (m then only feeds the tile-shape heuristics: pass the expected row count).
+   *   out_group_base / out_group_row0 (LINEAR): row r of group g is stored at
+   *                 (bf16*)out_group_base[g] + (out_group_row0[g] + r) * ldo — e.g. the SOURCE rank's combine buffer, so the
+   *                 fc2 epilogue IS the return all-to-all (16-byte stores through NVSwitch). */
+  const int32_t* group_counts;
+  int64_t a_rows;
+  const void* out_group_base;      /* uint64 device addresses [G] */
+  const int32_t* out_group_row0;   /* [G] */
 } aria_gemm_desc_t;
 
 /* Generic entry.  Replaces: torch F.linear / cuBLAS on the path, and grouped_gemm.ops.gmm. */
@@ -211,6 +222,13 @@ int aria_ep_layout(const int32_t* counts_all, int32_t rank, int32_t W, int32_t E
 int aria_scatter_rows_grouped(const void* rows, const int32_t* src_token, const int32_t* group_offsets, int32_t G,
                               const int32_t* dst_row_base, int32_t group_div, const uint64_t* peer_bufs, int32_t d,
                               int64_t max_rows, aria_stream_t stream);
+/* Fused exchange (fixed-capacity regions; see csrc/ep.cu): gathers the token rows in expert order (src_token / offsets from
+ * aria_build_permutation) and stores each into region (rank, e % E_loc) of owner e / E_loc — peer_recv[p] = rank p's receive
+ * buffer [W*E_loc][cap][d] as mapped on this GPU — and publishes per-block (row count, first sorted row) into the owners'
+ * meta arrays peer_counts[p] / peer_row0[p] ([W*E_loc] int32 each).  A peer barrier must follow before the owner reads. */
+int aria_ep_dispatch(const void* x, const int32_t* src_token, const int32_t* offsets, const uint64_t* peer_recv,
+                     const uint64_t* peer_counts, const uint64_t* peer_row0, int32_t rank, int32_t W, int32_t E,
+                     int32_t cap, int32_t d, int64_t max_rows, aria_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention (tcgen05 QK^T / PV, fp32 online softmax)

@@ -78,7 +78,7 @@ def test_routing_bit_exact(T, E, k):
     assert int(c.sum()) == T * k
 
 
-@pytest.mark.parametrize("T,E,k,d", [(1, 8, 2, 256), (37, 8, 2, 256), (768, 64, 6, 2560), (3001, 64, 6, 512)])
+@pytest.mark.parametrize("T,E,k,d", [(1, 8, 2, 256), (37, 8, 2, 256), (768, 64, 6, 2560), (3001, 64, 6, 512), (5461, 64, 6, 256), (5600, 64, 6, 256)])  # last: > 32768 ids -> the multi-block sort
 def test_permutation_and_combine_bit_exact(T, E, k, d):
     """stable argsort / index_select / index_copy_ / weighted sum (moe_lm.py:313-365)."""
     O, _ = _oracle()
