@@ -29,7 +29,10 @@ constexpr int A3_BM = 128, A3_BN = 128;
 constexpr int A3_THREADS = 384;  // WG0: warp 0 TMA, warp 1 / 2 MMA issuers of tile 0 / 1, warp 3 TMEM owner; WG1 / WG2: softmax tile 0 / 1
 // ---- build-time switches (scripts/build_variant.sh; measurements in profiles/r02_attention_notes.txt)
 #ifndef ARIA_ATTN_PF16
-#define ARIA_ATTN_PF16 1    // P as packed fp16 straight out of ex2.approx.f16x2 (one MUFU op per two keys); 0: fp32 ex2 + bf16 pack
+#define ARIA_ATTN_PF16 0    // 1 = P as packed fp16 from ex2.approx.f16x2 with a (fp16 A, bf16 B) PV descriptor. DEAD END, kept as a record:
+                            // B200 raises cudaErrorIllegalInstruction on a kind::f16 MMA whose A and B formats differ
+                            // (gpurun_out/r02 run 9), and ptxas lowers ex2.approx.f16x2 to TWO MUFU.EX2.F16 + PRMT, so it would
+                            // not have halved the MUFU work either.  0: fp32 ex2 + bf16 pack
 #endif
 #ifndef ARIA_ATTN_POLY
 #define ARIA_ATTN_POLY 0    // (PF16 = 0 only) of every 16 exponent pairs, how many go through exp2_poly2 instead of MUFU (0..16)
