@@ -54,6 +54,8 @@ SIGNATURES = {
     "aria_route_given_indices": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "aria_build_permutation": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "aria_grouped_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i64, i64, i64, i32, i32, vp]),
+    "aria_moe_block_fwd_workspace_bytes": (i64, [i64, i32, i32, i32, i32, i32]),
+    "aria_moe_block_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, i64, vp, vp]),
     "aria_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
     "aria_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "aria_combine_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
@@ -107,7 +109,7 @@ def load():
 
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; memsets are not counted)
-KERNELS_PER_CALL = {"router_topk": 2, "attention_decode": 2}
+KERNELS_PER_CALL = {"router_topk": 2, "attention_decode": 2, "moe_block_fwd": 9}
 # kernels exported for A/B measurements only (scripts/), not part of include/aria_b200.h
 EXTRA_SIGNATURES = {
     "aria_attention_fwd_v2": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, f32, i32, vp]),

@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -238,6 +240,17 @@ def shared_expert_overlapped(fn, like: torch.Tensor):
     return out, side
 
 
+def _side_stream(dev):
+    """The per-device side stream of the shared-expert branch (None when ARIA_MOE_SIDE_STREAM=0: branch runs in line)."""
+    import os
+    if os.environ.get("ARIA_MOE_SIDE_STREAM", "1") == "0":
+        return None
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return side
+
+
 def join_side(forked, like: torch.Tensor):
     """Second half of `shared_expert_overlapped`: make the current stream wait for the side branch; returns its result."""
     if isinstance(forked, tuple):
@@ -261,6 +274,16 @@ class MoELayer(nn.Module):
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if self.expert_parallel is not None:
             return self.expert_parallel(hidden_states)
+        if (hidden_states.is_cuda and type(self.experts.fc1) is GroupedGEMM and type(self.experts.fc2) is GroupedGEMM
+                and os.environ.get("ARIA_MOE_BLOCK", "1") != "0"):   # =0: one C-ABI call per kernel (bench.py's per-kernel table)
+            # the whole block behind one C-ABI call (csrc/moe_block.cu); shared experts on the side stream of this device
+            x = hidden_states.reshape(-1, hidden_states.shape[-1])
+            se = self.shared_experts
+            out = ops.moe_block_fwd(x, self.router.weight, self.experts.fc1.weight, self.experts.fc2.weight, se.gate_proj.weight,
+                                    se.up_proj.weight, se.down_proj.weight, self.router.config.moe_topk,
+                                    forced_top_idx=self.router.forced_top_indices, side_stream=_side_stream(x.device))
+            return out.view(hidden_states.shape)
+        # module-by-module path (adapter-wrapped experts, CPU stand-in ops of the host-logic tests)
         forked = shared_expert_overlapped(lambda: self.shared_experts(hidden_states), hidden_states)
         scores, indices, tokens_per_expert = self.router(hidden_states)
         permuted_tokens = self.token_dispatcher.token_permutation(hidden_states, indices, tokens_per_expert)

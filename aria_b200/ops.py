@@ -429,6 +429,33 @@ def unpermute_combine(y: torch.Tensor, dest_row: torch.Tensor, scores: torch.Ten
     return out
 
 
+def moe_block_fwd(x: torch.Tensor, w_router: torch.Tensor, fc1_w: torch.Tensor, fc2_w: torch.Tensor, gate_w: Optional[torch.Tensor],
+                  up_w: Optional[torch.Tensor], down_w: Optional[torch.Tensor], k: int,
+                  forced_top_idx: Optional[torch.Tensor] = None, side_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """MoELayer.forward (moe_lm.py:548-577) as one C-ABI call (`aria_moe_block_fwd`): x [T, d] -> [T, d]."""
+    _chk(x), _chk(w_router), _chk(fc1_w), _chk(fc2_w)
+    T, d = x.shape
+    E, I = fc2_w.shape[0], fc2_w.shape[1]
+    assert w_router.shape == (E, d) and fc1_w.shape == (E, d, 2 * I) and fc2_w.shape == (E, I, d)
+    Is = 0
+    if gate_w is not None:
+        _chk(gate_w), _chk(up_w), _chk(down_w)
+        Is = gate_w.shape[0]
+        assert gate_w.shape == (Is, d) and up_w.shape == (Is, d) and down_w.shape == (d, Is)
+    if forced_top_idx is not None:
+        _chk(forced_top_idx, torch.int32, align=4)
+        assert forced_top_idx.shape == (T, k)
+    lib = L.load()
+    nbytes = lib.aria_moe_block_fwd_workspace_bytes(T, d, E, k, I, Is)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty((T, d), dtype=bf16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.aria_moe_block_fwd(_p(x), _p(w_router), _p(fc1_w), _p(fc2_w), _p(gate_w), _p(up_w), _p(down_w), _p(out), T, d, E, k,
+                                       I, Is, _p(forced_top_idx), _p(ws), nbytes, _stream(x),
+                                       C.c_void_p(side_stream.cuda_stream) if side_stream is not None else None), "moe_block_fwd")
+    return out
+
+
 def offsets_from_counts(counts: torch.Tensor) -> torch.Tensor:
     _chk(counts, torch.int64)
     off = torch.empty((counts.numel() + 1,), dtype=torch.int32, device=counts.device)

@@ -220,11 +220,28 @@ class KernelTable:
     def __enter__(self):
         for n in self.names:
             setattr(self.ops, n, self._wrap(n, self.orig[n]))
+        # events time what runs between them ON ONE STREAM: the shared-expert branch, which the product runs on a side stream
+        # in parallel with the routed experts (moe_lm.shared_expert_overlapped), is run in line during this pass - otherwise
+        # its two GEMMs would be charged with the expert GEMMs they overlap (seen in profiles/r02_bench_a.json: a 13 GFLOP
+        # GEMM "taking" 219 us)
+        self._side = os.environ.get("ARIA_MOE_SIDE_STREAM")
+        os.environ["ARIA_MOE_SIDE_STREAM"] = "0"
+        # ... and the MoE block runs kernel by kernel (one ops call each) instead of through aria_moe_block_fwd
+        self._blk = os.environ.get("ARIA_MOE_BLOCK")
+        os.environ["ARIA_MOE_BLOCK"] = "0"
         return self
 
     def __exit__(self, *exc):
         for n in self.names:
             setattr(self.ops, n, self.orig[n])
+        if self._side is None:
+            os.environ.pop("ARIA_MOE_SIDE_STREAM", None)
+        else:
+            os.environ["ARIA_MOE_SIDE_STREAM"] = self._side
+        if self._blk is None:
+            os.environ.pop("ARIA_MOE_BLOCK", None)
+        else:
+            os.environ["ARIA_MOE_BLOCK"] = self._blk
 
     def table(self, steps, step_ms, peaks, sustained=True, top=14):
         pk_tf = peaks["bf16_tflops_sustained" if sustained and "bf16_tflops_sustained" in peaks else "bf16_tflops"]

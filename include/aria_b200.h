@@ -148,6 +148,21 @@ int aria_permute_rows(const void* x, const int32_t* src_token, void* permuted, i
 int aria_unpermute_combine(const void* y, const int32_t* dest_row, const void* scores, const void* shared,
                            void* out, int64_t T, int32_t d, int32_t k, aria_stream_t stream);
 
+/* MoELayer.forward as ONE call (moe_lm.py:548-577; SURVEY.md §8b "moe_block_fwd"): router -> stable sort by expert ->
+ * grouped fc1 + glu -> grouped fc2 -> unpermute + score-weighted sum + shared experts.  Launches the kernels of the entries
+ * above in order from C (no Python between them), the shared-expert branch on `side_stream` when one is given (forked from /
+ * joined to `stream` with events: becomes a parallel branch under CUDA-graph capture), counts and offsets never leave the
+ * device (the reference's tokens_per_expert.cpu(), moe_lm.py:478, is gone).
+ *   x [T, d]; w_router [E, d]; fc1_w [E, d, 2I] / fc2_w [E, I, d] (GroupedGEMM.weight layout); gate_w / up_w [I_shared, d],
+ *   down_w [d, I_shared] (nn.Linear layout; I_shared = 0: no shared experts); out [T, d]; all bf16.
+ *   forced_top_idx [T, k] int32 or NULL: expert choice given (parity / replay hook, see aria_route_given_indices).
+ *   workspace: aria_moe_block_fwd_workspace_bytes(...) bytes, 16-byte aligned; holds every intermediate. */
+int64_t aria_moe_block_fwd_workspace_bytes(int64_t T, int32_t d, int32_t E, int32_t k, int32_t I, int32_t I_shared);
+int aria_moe_block_fwd(const void* x, const void* w_router, const void* fc1_w, const void* fc2_w, const void* gate_w,
+                       const void* up_w, const void* down_w, void* out, int64_t T, int32_t d, int32_t E, int32_t k, int32_t I,
+                       int32_t I_shared, const int32_t* forced_top_idx, void* workspace, int64_t workspace_bytes,
+                       aria_stream_t stream, aria_stream_t side_stream);
+
 /* ---- backward of the MoE block (BASELINE cfg 5; autograd through moe_lm.py:548-577) ---- */
 /* h = bf16(bf16(silu(g)) * u) with g = h1[:, :I], u = h1[:, I:]  (unfused `glu`, moe_lm.py:505-507; training keeps h1). */
 int aria_swiglu_fwd(const void* h1, void* h, int64_t rows, int32_t I, aria_stream_t stream);

@@ -8,7 +8,7 @@ B=aria_b200/build
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
   -c aria_b200/csrc/$src -o $B/${src%.cu}_$name.o
 objs=""
-for o in gemm gemm2 gemm_wgrad moe_route moe_bwd ep elementwise attention attention_v3; do
+for o in gemm gemm2 gemm_wgrad moe_route moe_block moe_bwd ep elementwise attention attention_v3; do
   if [ "$o.cu" == "$src" ]; then objs="$objs $B/${o}_$name.o"; else objs="$objs $B/$o.o"; fi
 done
 nvcc -shared -o $B/libaria_$name.so $objs -gencode arch=compute_100a,code=sm_100a

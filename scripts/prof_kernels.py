@@ -8,7 +8,15 @@ from aria_b200 import ops, _lib as L
 dev = "cuda"
 mode = sys.argv[1]
 torch.manual_seed(0)
-if mode in ("attn", "attn_causal"):
+if mode == "attn72":   # the ViT shape as the model runs it: 16 heads x 4900 x 4900, head dim 72 carried in 128-wide rows
+    B, H, T, hd = 1, 16, 4900, 72
+    q = torch.zeros(B, H, T, 128, device=dev, dtype=torch.bfloat16)
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    for t in (q, k, v):
+        t[..., :hd] = torch.randn(B, H, T, hd, device=dev).bfloat16()
+    for _ in range(2):
+        ops.attention(q, k, v, T, T, hd ** -0.5, False, out_hd=hd)
+elif mode in ("attn", "attn_causal"):
     B, H, T = (1, 16, 4900) if mode == "attn" else (1, 20, 8192)
     q = torch.randn(B, H, T, 128, device=dev).bfloat16()
     k = torch.randn(B, H, T, 128, device=dev).bfloat16()

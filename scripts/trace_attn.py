@@ -18,7 +18,7 @@ vp = lambda t: C.c_void_p(t.data_ptr())
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(3):
     rc = lib.aria_attention_fwd(vp(q), vp(k), vp(v), vp(out), None, B, H, T, T, q.stride(0), q.stride(1), k.stride(0), k.stride(1), hd,
-                                hd ** -0.5, 0, vp(ws), 148 * 256 * 82 * 4, st)
+                                hd ** -0.5, 0, vp(ws), 148 * 256 * 84 * 4, st)
     assert rc == 0
 torch.cuda.synchronize()
 tr = ws[3200000:3200000 + 80].cpu().tolist()
@@ -32,3 +32,12 @@ for base, (who, labels) in names.items():
     tot = tr[base + 12]
     parts = ", ".join(f"{l} {tr[base + i] / 1e3:.1f}k" for i, l in enumerate(labels) if l != "-")
     print(f"  {who:24s} total {tot / 1e3:8.1f}k clk | {parts}")
+
+pc = ws[3300000:3300000 + 4 * 148].view(torch.int32).cpu().view(148, 4).long()
+g0, g1, clk, smid = pc[:, 0] & 0xffffffff, pc[:, 1] & 0xffffffff, pc[:, 2] & 0xffffffff, pc[:, 3]
+t0 = int(g0.min())
+dur = ((g1 - g0) & 0xffffffff).float() / 1e3
+print(f"  per-CTA (148): start spread {float((g0 - t0).max()) / 1e3:.1f} us; duration us min {float(dur.min()):.1f} median {float(dur.median()):.1f} max {float(dur.max()):.1f}; "
+      f"kernel span {float(((g1 - t0) & 0xffffffff).max()) / 1e3:.1f} us; clk/ns {float((clk.float() / (dur * 1e3)).median()):.3f}")
+order = dur.argsort()
+print("  slowest CTAs (cta, sm, us):", [(int(i), int(smid[i]), round(float(dur[i]), 1)) for i in order[-6:]], " fastest:", [(int(i), int(smid[i]), round(float(dur[i]), 1)) for i in order[:4]])
