@@ -635,6 +635,10 @@ static int launch_attn3(const void* q, const void* k, const void* v, Attn3Params
 
 using namespace aria;
 
+extern "C" int aria_attention_fwd_v2(const void* q, const void* k, const void* v, void* out, const uint8_t* key_mask, int32_t B, int32_t H,
+                                     int32_t Tq, int32_t Tk, int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b,
+                                     int64_t kv_stride_h, int32_t out_hd, float scale, int32_t causal, aria_stream_t stream_);  // attention.cu
+
 extern "C" int64_t aria_attention_fwd_workspace_bytes(int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t out_hd, int32_t causal) {
   (void)B; (void)H; (void)Tq; (void)Tk; (void)causal;
   // stream-K pieces of a persistent (non-causal) launch: at most one slot per CTA, 256 rows x (HD + 4) floats
@@ -651,6 +655,11 @@ extern "C" int aria_attention_fwd(const void* q, const void* k, const void* v, v
   ARIA_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk > 0 && Tk >= (causal ? Tq : 0));
   ARIA_CHECK_ARG(out_hd > 0 && out_hd <= 128 && out_hd % 8 == 0);
   ARIA_CHECK_ARG(q_stride_b % 8 == 0 && q_stride_h % 8 == 0 && kv_stride_b % 8 == 0 && kv_stride_h % 8 == 0);
+  // short causal launches (the 768-token LM prefill: 60 units of <= 6 key blocks) are prologue-bound; the round-1 kernel, with
+  // its lighter set-up, measures 23.3 us against 27.8 us there (profiles/r02_attn_v3_vs_v2.txt), and 1 % slower at T = 8192
+  if (causal && Tk <= 1024 && static_cast<int64_t>(B) * H * ((Tq + 2 * A3_BM - 1) / (2 * A3_BM)) <= sm_count())
+    return aria_attention_fwd_v2(q, k, v, out, key_mask, B, H, Tq, Tk, q_stride_b, q_stride_h, kv_stride_b, kv_stride_h, out_hd, scale,
+                                 causal, stream_);
   Attn3Params p{};
   p.B = B;
   p.H = H;

@@ -82,6 +82,63 @@ __global__ void __launch_bounds__(128) rmsnorm_kernel(const uint4* __restrict__ 
   }
 }
 
+// nn.LayerNorm, one WARP per row (rows of up to 32 * MAXV uint4 = 256 * MAXV elements): the row lives in the lanes' registers,
+// mean and variance are two shuffle reductions, no shared memory and no block barrier.  Used for the ViT (d = 1152: 144 vectors,
+// 4.5 per lane); the block-per-row kernel below spent its time in three __syncthreads per row with 16 of 128 threads active in
+// the second vector round (12.7 us per launch for 22.6 MB = 28 % of the HBM roofline in profiles/r02_bench_b.json).
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
+                                                             const uint4* __restrict__ b, uint4* __restrict__ out, int64_t rows,
+                                                             int vpr, float eps, float inv_d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float h[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vpr) {
+      const uint4 q = x[r * vpr + v];
+      const uint32_t a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[i][2 * j] = bf16_lo(a[j]);
+        h[i][2 * j + 1] = bf16_hi(a[j]);
+        s += h[i][2 * j] + h[i][2 * j + 1];
+      }
+    }
+  }
+  const float mean = warp_sum(s) * inv_d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + i * 32 < vpr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = h[i][j] - mean;
+        ss += dlt * dlt;
+      }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) * inv_d + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vpr) {
+      const uint4 qw = __ldg(w + v), qb = __ldg(b + v);
+      const uint32_t aw[4] = {qw.x, qw.y, qw.z, qw.w}, ab[4] = {qb.x, qb.y, qb.z, qb.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[2 * j] = (h[i][2 * j] - mean) * rstd * bf16_lo(aw[j]) + bf16_lo(ab[j]);
+        o[2 * j + 1] = (h[i][2 * j + 1] - mean) * rstd * bf16_hi(aw[j]) + bf16_hi(ab[j]);
+      }
+      out[r * vpr + v] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
 // nn.LayerNorm over the last dim: fp32 mean / variance (two-pass over registers), one rounding at the end.
 // One 128-thread block per row (same reasoning as rmsnorm_kernel).
 template <int MAXV>
@@ -276,6 +333,12 @@ extern "C" int aria_layernorm(const void* x, const void* weight, const void* bia
   ARIA_CHECK_ARG(x && weight && bias && out && d % 8 == 0 && d <= 128 * 8 * 4 && rows >= 0);
   if (rows == 0) return ARIA_OK;
   const int vpr = d / 8;
+  if (vpr <= 160 && rows >= 1024) {  // many short rows (the ViT): one warp per row
+    layernorm_warp_kernel<5><<<static_cast<int>((rows + 7) / 8), 256, 0, stream>>>(
+        static_cast<const uint4*>(x), static_cast<const uint4*>(weight), static_cast<const uint4*>(bias), static_cast<uint4*>(out), rows,
+        vpr, eps, 1.0f / d);
+    return check_launch("layernorm_warp_kernel");
+  }
   int64_t grid64 = rows;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (grid64 > cap) grid64 = cap;

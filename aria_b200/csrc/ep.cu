@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256) scatter_rows_grouped_kernel(const uint4* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Fused exchange (round 2).  Every owner rank p keeps, per (source rank s, local expert el), a FIXED-CAPACITY region of `cap`
+// Fused exchange (round 2).  Every owner rank p keeps, per (local expert el, source rank s) - region index el * W + s, so that the
+// W regions that are multiplied by the same expert's weights are neighbours in the grouped GEMM's tile order and the weights are
+// read from HBM once (cfg 2: the expert GEMMs are weight-streaming bound) - a FIXED-CAPACITY region of `cap`
 // rows in its receive buffer (a token picks an expert at most once, so cap = T_max bounds it): a sender needs nobody else's
 // counts to know where its rows go.  ep_dispatch gathers the token rows in expert order and stores each straight into the
 // owner's region over NVLink (fused permute + dispatch), and publishes (count, first sorted row) of each of its blocks into
@@ -117,12 +119,13 @@ __global__ void __launch_bounds__(256) ep_dispatch_kernel(const uint4* __restric
                                                           const int32_t* __restrict__ offsets, const uint64_t* __restrict__ peer_recv,
                                                           const uint64_t* __restrict__ peer_counts, const uint64_t* __restrict__ peer_row0,
                                                           int rank, int E, int E_loc, int cap, int vec_per_row) {
+  const int W = E / E_loc;
   __shared__ int s_off[1025];
   for (int i = threadIdx.x; i <= E; i += blockDim.x) s_off[i] = offsets[i];
   __syncthreads();
   if (blockIdx.x == 0) {  // meta: my block for global expert e = group (rank, e % E_loc) of owner e / E_loc
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      const int p = e / E_loc, g = rank * E_loc + (e - p * E_loc);
+      const int p = e / E_loc, g = (e - p * E_loc) * W + rank;
       reinterpret_cast<int32_t*>(peer_counts[p])[g] = s_off[e + 1] - s_off[e];
       reinterpret_cast<int32_t*>(peer_row0[p])[g] = s_off[e];
     }
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(256) ep_dispatch_kernel(const uint4* __restric
     }
     const int e = lo, p = e / E_loc, el = e - p * E_loc;
     uint4* dst = reinterpret_cast<uint4*>(peer_recv[p]) +
-                 (static_cast<int64_t>(rank * E_loc + el) * cap + (r - s_off[e])) * vec_per_row;
+                 (static_cast<int64_t>(el * W + rank) * cap + (r - s_off[e])) * vec_per_row;
     const int st = src_token[r];
     if (st < 0) {  // alignment pad row of the training layout: zeros
       for (int v = lane; v < vec_per_row; v += 32) dst[v] = make_uint4(0, 0, 0, 0);

@@ -86,7 +86,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int a_row = row0 + m_idx * BM;
-        const int bgrp = p.group_mod ? grp % p.group_mod : grp;
+        const int bgrp = weight_block(p, grp);
         // B coordinates of this tile (k-invariant part)
         int b_c0 = 0, b_c1 = 0;          // K-major: row (n) coordinate of the two boxes; MN-major: base k row
         const CUtensorMap* tb0 = &tmB0;
@@ -242,7 +242,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   ARIA_CHECK_ARG(d->m >= 0 && d->n > 0 && d->k > 0);
   ARIA_CHECK_ARG(d->n % 8 == 0 && d->k % 8 == 0 && d->lda % 8 == 0);
   ARIA_CHECK_ARG(d->n_seg >= 1 && d->n_seg <= 3);
-  ARIA_CHECK_ARG(d->num_groups >= 1 && d->group_mod >= 0);
+  ARIA_CHECK_ARG(d->num_groups >= 1 && (d->group_mod >= 0 || d->num_groups % (-d->group_mod) == 0));
   ARIA_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out[0]) & 15) == 0);
   if (d->m == 0) return ARIA_OK;
   const bool b_mn = d->b_layout == ARIA_B_GKN;
@@ -377,7 +377,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   if (rc) return rc;
   if (b_mn) {
     const uint64_t ncols = swiglu ? 2 * d->n : d->n;
-    const uint64_t n_weights = d->group_mod > 0 ? d->group_mod : d->num_groups;
+    const uint64_t n_weights = d->group_mod > 0 ? d->group_mod : (d->group_mod < 0 ? d->num_groups / (-d->group_mod) : d->num_groups);
     rc = make_tmap_2d(&tmB[0], d->b[0], ncols, n_weights * d->k, ncols * 2, 64, BK);
     if (rc) return rc;
     tmB[1] = tmB[0];
@@ -389,7 +389,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     if (two_cta && !swiglu) box_rows = BN / 2;
     for (int s = 0; s < 3; ++s) {
       const void* ptr = s < nb ? d->b[s] : d->b[0];
-      const uint64_t b_rows = b_gnk ? static_cast<uint64_t>(d->group_mod > 0 ? d->group_mod : d->num_groups) * d->n : d->n;
+      const uint64_t b_rows = b_gnk ? static_cast<uint64_t>(d->group_mod > 0 ? d->group_mod : (d->group_mod < 0 ? d->num_groups / (-d->group_mod) : d->num_groups)) * d->n : d->n;
       rc = make_tmap_2d(&tmB[s], ptr, d->k, b_rows, d->k * 2, BK, box_rows);
       if (rc) return rc;
     }

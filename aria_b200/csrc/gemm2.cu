@@ -86,7 +86,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
         const int a_row = row0 + m_idx * BM2 + static_cast<int>(rank) * BM;
-        const int bgrp = p.group_mod ? grp % p.group_mod : grp;
+        const int bgrp = weight_block(p, grp);
         int b_c = 0;
         const CUtensorMap* tb = &tmB0;
         if constexpr (B_MN) {

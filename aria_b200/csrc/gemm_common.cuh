@@ -33,7 +33,8 @@ struct GemmParams {
   const uint64_t* out_group_base;  // non-NULL (LINEAR): rows of group g are stored at out_group_base[g] + (out_group_row0[g] + r)*ldo
   const int32_t* out_group_row0;   //   — e.g. straight into the source rank's combine buffer over NVLink (expert parallelism)
   int b_group_rows;  // K-major grouped weights [G, N, K]: B row of (group g, column c) is g*b_group_rows + c (0: dense)
-  int group_mod;  // weight block of group g is g % group_mod (0: identity) — expert-parallel (src rank, expert) groups
+  int group_mod;  // weight block of group g: g % group_mod (> 0: expert-parallel (source rank, expert) groups), g / -group_mod (< 0:
+                  // (expert, source rank) groups - the groups of one expert are neighbours and share its weights in L2), g (0)
   int n_seg;
   int act;
   const __nv_bfloat16* bias[3];
@@ -49,6 +50,10 @@ struct GemmParams {
   const int32_t* position_ids;
   int dbg_lbo, dbg_sbo, dbg_kadv;
 };
+
+ARIA_DEVICE int weight_block(const GemmParams& p, int grp) {
+  return p.group_mod > 0 ? grp % p.group_mod : (p.group_mod < 0 ? grp / (-p.group_mod) : grp);
+}
 
 // Monotonic decoder of the persistent tile index -> (group, m-tile, n-tile).  Tiles are ordered group-major,
 // then n-tile, with the m-tile innermost so that CTAs running concurrently share the same weight tile.
@@ -170,24 +175,45 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
     __nv_bfloat16* orow = p.out[0] + grow * p.ldo + col0;
     if (p.out_group_base)  // per-group destination (possibly a peer GPU's memory: the stores then travel over NVLink)
       orow = reinterpret_cast<__nv_bfloat16*>(p.out_group_base[grp]) + static_cast<int64_t>(p.out_group_row0[grp] + r_in_grp) * p.ldo + col0;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + grow * p.ldr + col0 : nullptr;
-    constexpr int NCH = BN / 32;
-    const int cb = (half * NCH / 2) * 32, ce = half ? BN : (NCH / 2) * 32;
-#pragma unroll 1
-    for (int c = cb; c < ce; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c, v);
+    const __nv_bfloat16* rrow = (p.residual && row_ok) ? p.residual + grow * p.ldr + col0 : nullptr;
+    // Two-deep software pipeline over the 32-column chunks of this warp's half: the accumulator chunk (tcgen05.ld), the bias
+    // vectors and the residual row pieces of chunk i + 1 are all in flight while chunk i is converted and stored.  Round 1
+    // loaded bias / residual inside the per-8-column loop, each load followed by its use: ncu showed 16 - 32 serial global-load
+    // latencies per thread and tile (long_scoreboard on the LDG consumers = 22 % of all samples of the ViT fc1 GEMM, tensor pipe
+    // 39 % active), i.e. the epilogue, not the MMA loop, set the tile time (profiles/r02_gemm_notes.txt).
+    constexpr int NCH = BN / 32, NCHH = NCH - NCH / 2;  // chunks of the tile / of the larger half (BN = 32: all in half 1)
+    const int cb = half ? (NCH / 2) * 32 : 0;
+    const int n_my = half ? NCH - NCH / 2 : NCH / 2;
+    if (n_my == 0) return;
+    uint32_t v[2][32];
+    uint4 bv[2][4], rv[2][4];
+    auto issue = [&](int c, int set) {
+      tmem_ld_32x32(taddr + c, v[set]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = col0 + c + q * 8;
+        const bool ok = col + 8 <= n_out_total;
+        bv[set][q] = (bias && ok) ? __ldg(reinterpret_cast<const uint4*>(bias + (col - seg * p.N))) : make_uint4(0, 0, 0, 0);
+        rv[set][q] = (rrow && ok) ? *reinterpret_cast<const uint4*>(rrow + c + q * 8) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    issue(cb, 0);
+#pragma unroll
+    for (int i = 0; i < NCHH; ++i) {
+      if (i >= n_my) break;
+      const int c = cb + i * 32;
+      const int set = i & 1;
       tmem_ld_wait();
+      if (i + 1 < n_my) issue(c + 32, set ^ 1);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int col = col0 + c + q * 8;
         if (col + 8 > n_out_total) continue;
         float x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[q * 8 + j]);
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[set][q * 8 + j]);
         if (bias) {
-          uint4 bv = *reinterpret_cast<const uint4*>(bias + (col - seg * p.N));
-          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+          const uint32_t bw[4] = {bv[set][q].x, bv[set][q].y, bv[set][q].z, bv[set][q].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             x[2 * j] += bf16_lo(bw[j]);
@@ -202,8 +228,7 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
         }
         if (row_ok) {
           if (rrow) {
-            uint4 rv = *reinterpret_cast<const uint4*>(rrow + c + q * 8);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t rw[4] = {rv[set][q].x, rv[set][q].y, rv[set][q].z, rv[set][q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               x[2 * j] += bf16_lo(rw[j]);
@@ -240,14 +265,21 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
         uint32_t lo[32], hi[32];
         tmem_ld_32x32(th + c, lo);
         tmem_ld_32x32(th + 64 + c, hi);
+        // all 16 table vectors of this chunk are requested before anything waits (they were loaded one group at a time
+        // inside the loop below, each followed by its use)
+        uint4 tc_lo[4], ts_lo[4], tc_hi[4], ts_hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tc_lo[q] = __ldg(reinterpret_cast<const uint4*>(cs + c + q * 8));
+          ts_lo[q] = __ldg(reinterpret_cast<const uint4*>(sn + c + q * 8));
+          tc_hi[q] = __ldg(reinterpret_cast<const uint4*>(cs + 64 + c + q * 8));
+          ts_hi[q] = __ldg(reinterpret_cast<const uint4*>(sn + 64 + c + q * 8));
+        }
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 c_lo = *reinterpret_cast<const uint4*>(cs + c + q * 8);
-            uint4 s_lo = *reinterpret_cast<const uint4*>(sn + c + q * 8);
-            uint4 c_hi = *reinterpret_cast<const uint4*>(cs + 64 + c + q * 8);
-            uint4 s_hi = *reinterpret_cast<const uint4*>(sn + 64 + c + q * 8);
+            const uint4 c_lo = tc_lo[q], s_lo = ts_lo[q], c_hi = tc_hi[q], s_hi = ts_hi[q];
             const uint32_t cl[4] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w}, sl[4] = {s_lo.x, s_lo.y, s_lo.z, s_lo.w};
             const uint32_t ch[4] = {c_hi.x, c_hi.y, c_hi.z, c_hi.w}, sh[4] = {s_hi.x, s_hi.y, s_hi.z, s_hi.w};
             float ol[8], oh[8];
@@ -280,9 +312,15 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
         } else {  // BN not a multiple of 32 (e.g. 144): the tail re-reads an overlapping window
           tmem_ld_32x32(taddr + BN - 32, v);
         }
-        tmem_ld_wait();
         const int cbase = (c + 32 <= BN) ? c : BN - 32;
         const int qstart = (c + 32 <= BN) ? 0 : (c - cbase) / 8;
+        uint4 bvq[4];  // the chunk's bias vectors, requested before the TMEM wait
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cs_ = cseg0 + cbase + q * 8;
+          bvq[q] = (bias && cs_ + 8 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(bias + cs_)) : make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q < qstart) continue;
@@ -292,7 +330,7 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[q * 8 + j]);
           if (bias) {
-            uint4 bv = *reinterpret_cast<const uint4*>(bias + cs_);
+            const uint4 bv = bvq[q];
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

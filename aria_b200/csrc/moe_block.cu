@@ -125,7 +125,8 @@ extern "C" int aria_moe_block_fwd(const void* x, const void* w_router, const voi
     if ((rc = aria_route_given_indices(at(ws.logits), forced_top_idx, at(ws.scores), counts, T, E, k, stream))) return rc;
     idx = const_cast<int32_t*>(forced_top_idx);
   } else {
-    if ((rc = aria_router_topk(x, w_router, nullptr, idx, at(ws.scores), counts, T, d, E, k, stream))) return rc;
+    // (aria_router_topk always materialises the bf16 logits: top-k runs on the ROUNDED values, moe_lm.py:200,261)
+    if ((rc = aria_router_topk(x, w_router, at(ws.logits), idx, at(ws.scores), counts, T, d, E, k, stream))) return rc;
   }
   if ((rc = aria_build_permutation(idx, counts, offsets, dest, src, T, E, k, 1, stream))) return rc;
   if ((rc = aria_permute_rows(x, src, at(ws.permuted), R, d, stream))) return rc;

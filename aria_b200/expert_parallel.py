@@ -168,7 +168,7 @@ class FusedPeerTransport:
     friendly.  Arena of every rank (mapped by all peers):
 
         meta_counts [W*E_loc] int32 | meta_row0 [W*E_loc] int32 | flags [W] int32
-        | recv_x [W*E_loc][cap][d] bf16 (region (s, el) = rows rank s routed to my expert el) | ret_y [T_max*k][d] bf16
+        | recv_x [E_loc*W][cap][d] bf16 (region el * W + s = rows rank s routed to my expert el) | ret_y [T_max*k][d] bf16
 
     cap = T_max rounded up to 16 (+16 for the training layout's alignment pads): a token picks an expert at most once."""
 
@@ -199,8 +199,8 @@ class FusedPeerTransport:
         self.recv_x = self.arena.local_view(self.off_recv, (self.G * self.cap, hidden), torch.bfloat16)
         self.ret_y = self.arena.local_view(self.off_ret, (self.ret_rows, hidden), torch.bfloat16)
         self.starts = (torch.arange(self.G, dtype=torch.int32) * self.cap).to(dev)
-        # group g = (source rank g // E_loc, local expert): its outputs go back into rank s's ret_y
-        self.out_base = self.p_ret.repeat_interleave(self.E_loc).contiguous()
+        # group g = (local expert g // W, source rank g % W): its outputs go back into rank s's ret_y
+        self.out_base = self.p_ret.repeat(self.E_loc).contiguous()
         self.h_buf = torch.empty((self.G * self.cap, inter), dtype=torch.bfloat16, device=dev)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.device = dev
@@ -234,9 +234,9 @@ def _ep_forward_fused(self, x: torch.Tensor) -> torch.Tensor:
                                      tr.E, tr.cap, tr.d, T * self.k, stream), "ep_dispatch")
     tr.barrier()
     ops.grouped_gemm_regions(tr.recv_x, self.w["experts.fc1.weight"], tr.starts, tr.meta_counts, T * self.k, swiglu=True,
-                             group_mod=tr.E_loc, out=tr.h_buf)
+                             group_mod=-tr.W, out=tr.h_buf)
     # fc2: every output row is stored by the GEMM epilogue straight into its SOURCE rank's combine buffer (the return all-to-all)
-    ops.grouped_gemm_regions(tr.h_buf, self.w["experts.fc2.weight"], tr.starts, tr.meta_counts, T * self.k, group_mod=tr.E_loc,
+    ops.grouped_gemm_regions(tr.h_buf, self.w["experts.fc2.weight"], tr.starts, tr.meta_counts, T * self.k, group_mod=-tr.W,
                              out_group_base=tr.out_base, out_group_row0=tr.meta_row0, ldo=tr.d)
     tr.barrier()
     shared = join_side(forked, x2)

@@ -40,6 +40,13 @@ def _moe_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
     shape = hidden_states.shape
     x = hidden_states.reshape(-1, shape[-1]).contiguous()
     se = self.shared_experts
+    if x.is_cuda:
+        # one C-ABI call for the whole block (aria_moe_block_fwd, csrc/moe_block.cu); the shared experts run on a side stream
+        out = ops.moe_block_fwd(x, self.router.weight, self.experts.fc1.weight, self.experts.fc2.weight, se.gate_proj.weight,
+                                se.up_proj.weight, se.down_proj.weight, cfg.moe_topk, side_stream=_m._side_stream(x.device))
+        return out.view(shape)
+    # kernel-by-kernel sequence (what the block entry launches); reached only by the host-logic tests, which swap `ops` for
+    # oracle-backed stand-ins on CPU (tests/standin_ops.py)
     forked = _m.shared_expert_overlapped(
         lambda: ops.linear(ops.linear_swiglu(x, se.gate_proj.weight, se.up_proj.weight), se.down_proj.weight), x)
     scores, idx, counts, _ = ops.router_topk(x, self.router.weight, cfg.moe_topk)

@@ -138,7 +138,7 @@ def grouped_gemm_regions(a_buf: torch.Tensor, b: torch.Tensor, starts: torch.Ten
                          out_group_base: Optional[torch.Tensor] = None, out_group_row0: Optional[torch.Tensor] = None,
                          ldo: Optional[int] = None) -> Optional[torch.Tensor]:
     """Grouped GEMM over FIXED-CAPACITY row regions (expert parallelism, csrc/ep.cu): group g = rows
-    [starts[g], starts[g] + counts[g]) of `a_buf`, multiplied by weight block g % group_mod.  `counts` may be written by peer
+    [starts[g], starts[g] + counts[g]) of `a_buf`, multiplied by weight block g % group_mod (group_mod > 0) or g // -group_mod (< 0).  `counts` may be written by peer
     GPUs (it is read on the device at launch).  rows_hint = expected total rows (tile-shape heuristics only).
     With out_group_base / out_group_row0 the rows of group g are stored at (bf16*)out_group_base[g] + (out_group_row0[g] + r)*ldo
     — e.g. straight into the source rank's combine buffer over NVLink — and nothing is returned."""
@@ -146,7 +146,7 @@ def grouped_gemm_regions(a_buf: torch.Tensor, b: torch.Tensor, starts: torch.Ten
     cap_rows, K = a_buf.shape
     E, Kb, Nb = b.shape
     G = starts.numel()
-    assert Kb == K and counts.numel() == G and (G == E if not group_mod else (group_mod == E and G % E == 0))
+    assert Kb == K and counts.numel() == G and (G == E if not group_mod else ((group_mod == E and G % E == 0) if group_mod > 0 else G == E * -group_mod))
     N = Nb // 2 if swiglu else Nb
     d = L.GemmDesc()
     d.a, d.lda, d.m, d.n, d.k = a_buf.data_ptr(), K, max(1, min(rows_hint, cap_rows)), N, K

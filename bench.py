@@ -148,6 +148,13 @@ def op_work(name, a, k):
         sw = bool(k.get("swiglu", a[3] if len(a) > 3 and name == "grouped_gemm" else False))
         No = Nb // 2 if sw else Nb
         return (f"{name}{'_swiglu' if sw else ''}[{R}rows,E{E},{K}->{Nb}]", 2 * R * K * Nb, bf * (E * K * Nb + R * K + R * No))
+    if name == "grouped_gemm_regions":   # expert parallelism: rows_hint rows spread over fixed-capacity regions, THIS rank's experts
+        x, w, rh = a[0], a[1], a[4]
+        K, E, Nb = x.shape[1], w.shape[0], w.shape[2]
+        sw = bool(k.get("swiglu", False))
+        No = Nb // 2 if sw else Nb
+        return (f"grouped_gemm_regions{'_swiglu' if sw else ''}[~{rh}rows,E{E}local,{K}->{Nb}]", 2 * rh * K * Nb,
+                bf * (E * K * Nb + rh * K + rh * No))
     if name == "grouped_wgrad":
         x, y = a[0], a[1]
         R, Md, Nd = x.shape[0], x.shape[1], y.shape[1]

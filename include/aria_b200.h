@@ -58,8 +58,10 @@ typedef struct aria_gemm_desc {
    * int32) are the row offsets of each expert's contiguous row block inside A / out.                   */
   int32_t num_groups;
   const int32_t* group_offsets;
-  int32_t group_mod;       /* GKN only: group g uses weight block g % group_mod (0 = identity). Expert parallelism
-                            * receives rows grouped by (source rank, local expert): num_groups = W*E_loc, mod = E_loc */
+  int32_t group_mod;       /* grouped weights: group g uses weight block g % group_mod (> 0), g / -group_mod (< 0), g (0).
+                            * Expert parallelism receives rows grouped by (source rank, local expert): num_groups = W*E_loc,
+                            * mod = E_loc; or by (local expert, source rank): mod = -W, which keeps the W groups that share
+                            * an expert's weights next to each other in the tile order (one HBM read, W-1 L2 hits) */
   /* epilogue */
   int32_t epilogue;
   int32_t act;
@@ -116,7 +118,7 @@ int aria_offsets_from_counts(const int64_t* counts, int32_t* offsets, int32_t nu
  * MoE routing / dispatch (HBM-bound kernels)
  * ------------------------------------------------------------------------------------------------ */
 /* TopKRouter.forward (moe_lm.py:275-293 = gating :190-201 + routing :261-269), eval path.
- *   x [T, d] bf16, w_router [E, d] bf16 -> logits [T, E] bf16 (optional, may be NULL),
+ *   x [T, d] bf16, w_router [E, d] bf16 -> logits [T, E] bf16 (required: the top-k runs on the rounded values),
  *   top_idx [T, k] int32 (descending logit, ties: lowest expert id), scores [T, k] bf16 (fp32 softmax over
  *   the k selected bf16 logits, rounded to bf16), counts [E] int32 (must be zeroed by this call: it is).
  * E <= 64, k <= 8. */
@@ -238,7 +240,7 @@ int aria_scatter_rows_grouped(const void* rows, const int32_t* src_token, const 
                               const int32_t* dst_row_base, int32_t group_div, const uint64_t* peer_bufs, int32_t d,
                               int64_t max_rows, aria_stream_t stream);
 /* Fused exchange (fixed-capacity regions; see csrc/ep.cu): gathers the token rows in expert order (src_token / offsets from
- * aria_build_permutation) and stores each into region (rank, e % E_loc) of owner e / E_loc — peer_recv[p] = rank p's receive
+ * aria_build_permutation) and stores each into region (e % E_loc, rank) = index (e % E_loc) * W + rank of owner e / E_loc — peer_recv[p] = rank p's receive
  * buffer [W*E_loc][cap][d] as mapped on this GPU — and publishes per-block (row count, first sorted row) into the owners'
  * meta arrays peer_counts[p] / peer_row0[p] ([W*E_loc] int32 each).  A peer barrier must follow before the owner reads. */
 int aria_ep_dispatch(const void* x, const int32_t* src_token, const int32_t* offsets, const uint64_t* peer_recv,

@@ -70,6 +70,18 @@ elif mode == "dense":
     b = torch.randn(4304, device=dev).bfloat16()
     for _ in range(3):
         ops.linear(x, w, b, act=L.ACT_GELU_TANH)
+elif mode == "dense_lm":   # LM o_proj / down_proj shape at the cfg-2 prefill: 768 tokens, 2560 x 2560
+    x = torch.randn(768, 2560, device=dev).bfloat16()
+    w = (torch.randn(2560, 2560, device=dev) * 0.02).bfloat16()
+    for _ in range(3):
+        ops.linear(x, w)
+elif mode == "dense_oproj":  # ViT o_proj: 4900 x 1152 x 1152 with residual
+    x = torch.randn(4900, 1152, device=dev).bfloat16()
+    w = (torch.randn(1152, 1152, device=dev) * 0.02).bfloat16()
+    b = torch.randn(1152, device=dev).bfloat16()
+    r = torch.randn(4900, 1152, device=dev).bfloat16()
+    for _ in range(3):
+        ops.linear(x, w, b, residual=r)
 elif mode == "dense_big":
     x = torch.randn(8192, 8192, device=dev).bfloat16()
     w = (torch.randn(8192, 8192, device=dev) * 0.02).bfloat16()

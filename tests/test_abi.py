@@ -69,6 +69,14 @@ def test_bad_arguments_are_errors_not_crashes(lib):
     assert lib.aria_router_aux_bwd(fake, fake, fake, 4, 300, 2, 0.1, 0.1, 1.0, None) == -1
     assert lib.aria_router_aux_loss(fake, fake, fake, 4, 8, 2, 0.1, 0.1, fake, 0, None) == -1   # workspace too small
     assert lib.aria_router_aux_workspace_bytes(64) % (65 * 4) == 0
+    # whole-block entry: workspace query, null pointers, too many experts, workspace too small — all before any CUDA call
+    nb = lib.aria_moe_block_fwd_workspace_bytes(768, 2560, 64, 6, 1664, 3328)
+    assert nb >= 2 * (768 * 6 * (2560 * 2 + 1664) + 768 * (3328 + 2560)) and nb % 256 == 0
+    assert lib.aria_moe_block_fwd_workspace_bytes(0, 2560, 64, 6, 1664, 3328) == -1
+    assert lib.aria_moe_block_fwd(None, None, None, None, None, None, None, None, 768, 2560, 64, 6, 1664, 3328, None, None, 0, None, None) == -1
+    assert lib.aria_moe_block_fwd(fake, fake, fake, fake, fake, fake, fake, fake, 768, 2560, 128, 6, 1664, 3328, None, fake, nb, None, None) == -1
+    assert lib.aria_moe_block_fwd(fake, fake, fake, fake, fake, fake, fake, fake, 768, 2560, 64, 6, 1664, 3328, None, fake, nb - 1, None, None) == -1
+    assert lib.aria_moe_block_fwd(fake, fake, fake, fake, None, None, None, fake, 768, 2560, 64, 6, 1664, 3328, None, fake, nb, None, None) == -1
     # GEMM descriptor validation: n must be a multiple of 8 (16-byte rows)
     d.a = d.b[0] = d.out[0] = 0x1000
     d.m, d.n, d.k, d.lda, d.n_seg, d.num_groups = 16, 12, 64, 64, 1, 1
