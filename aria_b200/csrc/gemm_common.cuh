@@ -154,9 +154,12 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        float g0 = bf16r(__uint_as_float(g[j])), g1 = bf16r(__uint_as_float(g[j + 1]));
-        float u0 = bf16r(__uint_as_float(u[j])), u1 = bf16r(__uint_as_float(u[j + 1]));
-        float s0 = bf16r(fast_silu(g0)), s1 = bf16r(fast_silu(g1));
+        float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
+        float u0 = __uint_as_float(u[j]), u1 = __uint_as_float(u[j + 1]);
+        bf16r2(g0, g1);
+        bf16r2(u0, u1);
+        float s0 = fast_silu(g0), s1 = fast_silu(g1);
+        bf16r2(s0, s1);
         o[j >> 1] = pack_bf16(s0 * u0, s1 * u1);
       }
       if (row_ok) {
@@ -285,14 +288,18 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
             float ol[8], oh[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float xl = bf16r(__uint_as_float(lo[q * 8 + j]));
-              float xh = bf16r(__uint_as_float(hi[q * 8 + j]));
+              float xl = __uint_as_float(lo[q * 8 + j]);
+              float xh = __uint_as_float(hi[q * 8 + j]);
+              bf16r2(xl, xh);
               float cosl = (j & 1) ? bf16_hi(cl[j >> 1]) : bf16_lo(cl[j >> 1]);
               float sinl = (j & 1) ? bf16_hi(sl[j >> 1]) : bf16_lo(sl[j >> 1]);
               float cosh_ = (j & 1) ? bf16_hi(ch[j >> 1]) : bf16_lo(ch[j >> 1]);
               float sinh_ = (j & 1) ? bf16_hi(sh[j >> 1]) : bf16_lo(sh[j >> 1]);
-              ol[j] = bf16r(xl * cosl) + bf16r(-xh * sinl);
-              oh[j] = bf16r(xh * cosh_) + bf16r(xl * sinh_);
+              float a0 = xl * cosl, a1 = -xh * sinl, b0 = xh * cosh_, b1 = xl * sinh_;
+              bf16r2(a0, a1);
+              bf16r2(b0, b1);
+              ol[j] = a0 + a1;
+              oh[j] = b0 + b1;
             }
             *reinterpret_cast<uint4*>(orow + c + q * 8) =
                 make_uint4(pack_bf16(ol[0], ol[1]), pack_bf16(ol[2], ol[3]), pack_bf16(ol[4], ol[5]), pack_bf16(ol[6], ol[7]));

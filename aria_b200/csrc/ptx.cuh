@@ -222,7 +222,10 @@ ARIA_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 ARIA_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses.  The explicit
+  // `.release.cluster` this carried in round 1 made ptxas emit MEMBAR.ALL.CTA + ERRBAR in front of every arrive (5 % of the samples
+  // of the ViT fc1 GEMM); what the arrive publishes are completed tcgen05.ld reads, ordered by tcgen05.fence::before_thread_sync.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared),
 // destination = this CTA's shared memory.
@@ -440,6 +443,16 @@ ARIA_DEVICE float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x
 ARIA_DEVICE uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Round TWO fp32 values to bf16 precision (RNE) in place with one F2FP pack + two bit moves: bf16r() compiles to one F2F per value,
+// which runs on the 16-lane XU pipe together with the MUFU ops of the fused activations (profiles/r02_gemm_notes.txt).
+// Measured (r02_gemm_notes.txt): neutral in the SwiGLU / RoPE epilogues, SLOWER in the bias + gelu epilogue (ViT fc1 54.6 -> 63.2 us),
+// where the scalar form is kept.
+ARIA_DEVICE void bf16r2(float& a, float& b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<uint32_t*>(&v);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xFFFF0000u);
 }
 ARIA_DEVICE float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 ARIA_DEVICE float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }

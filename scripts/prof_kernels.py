@@ -82,6 +82,32 @@ elif mode == "dense_oproj":  # ViT o_proj: 4900 x 1152 x 1152 with residual
     r = torch.randn(4900, 1152, device=dev).bfloat16()
     for _ in range(3):
         ops.linear(x, w, b, residual=r)
+elif mode in ("ep_fc1_expert_major", "ep_fc1_source_major"):
+    # the fc1 grouped GEMM of one rank of a W=2 expert-parallel cfg-2 prefill: 32 local experts x 2 source ranks = 64 fixed-capacity
+    # regions with ~72 rows each; region order (expert, source) [group_mod = -W] vs (source, expert) [group_mod = E_loc]
+    W_, E_loc, d, I, cap = 2, 32, 2560, 1664, 784
+    G = W_ * E_loc
+    g = torch.Generator().manual_seed(3)
+    counts = torch.randint(50, 95, (G,), generator=g).to(torch.int32).to(dev)
+    starts = (torch.arange(G, dtype=torch.int32) * cap).to(dev)
+    w = (torch.randn(E_loc, d, 2 * I, device=dev) * 0.02).bfloat16()
+    a = torch.randn(G * cap, d, device=dev).bfloat16()
+    out = torch.empty(G * cap, I, device=dev, dtype=torch.bfloat16)
+    gm = -W_ if mode == "ep_fc1_expert_major" else E_loc
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ops.grouped_gemm_regions(a, w, starts, counts, 4608, swiglu=True, group_mod=gm, out=out)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0.record()
+        ops.grouped_gemm_regions(a, w, starts, counts, 4608, swiglu=True, group_mod=gm, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    print(mode, "us per launch (L2 flushed):", [round(t, 1) for t in ts], "weights MB", w.numel() * 2 / 1e6)
 elif mode == "dense_big":
     x = torch.randn(8192, 8192, device=dev).bfloat16()
     w = (torch.randn(8192, 8192, device=dev) * 0.02).bfloat16()
