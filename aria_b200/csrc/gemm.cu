@@ -275,6 +275,7 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   p.out_group_base = static_cast<const uint64_t*>(d->out_group_base);
   p.out_group_row0 = d->out_group_row0;
   p.group_mod = d->group_mod;
+  p.pair = 0;
   p.b_group_rows = b_gnk ? static_cast<int>(d->n) : 0;
   p.n_seg = swiglu ? 1 : d->n_seg;
   p.act = d->act;
@@ -348,6 +349,18 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     }
   }
 
+  // Expert-parallel regions ordered (expert, source rank) with an even number of source ranks: CTA pairs over neighbouring regions
+  // (gemm2.cu pair mode; ARIA_GEMM_PAIR=0 keeps the 1-CTA kernel for A/B measurements)
+  {
+    static const bool pair_on = [] { const char* e = getenv("ARIA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    const bool ok = swiglu ? (d->n % 128 == 0) : (d->n % 256 == 0);
+    if (pair_on && d->group_counts && d->group_mod < 0 && (-d->group_mod) % 2 == 0 && b_mn && ok && d->epilogue != ARIA_EPI_HEADS) {
+      two_cta = true;
+      BN = 256;
+      p.pair = 1;
+    }
+  }
+
   // HBM-bound grouped regime on the 1-CTA kernel (few rows per expert): 128 x 256 tiles halve the A-tile share of the
   // L2 -> SM traffic per streamed weight byte (env ARIA_GEMM_WIDE=0 disables, for A/B measurements)
   if (!two_cta && b_mn && d->num_groups > 1 && BN == 128) {
@@ -398,7 +411,8 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   const int out_bn = swiglu ? BN / 2 : BN;
   const int64_t n_tiles = (n_out_total + out_bn - 1) / out_bn;
   const int bm = two_cta ? 2 * BM : BM;
-  const int64_t m_tiles_ub = (d->m + bm - 1) / bm + (d->num_groups > 1 ? d->num_groups : 0);
+  const int64_t m_tiles_ub = p.pair ? (d->m + BM - 1) / BM + d->num_groups / 2
+                                    : (d->m + bm - 1) / bm + (d->num_groups > 1 ? d->num_groups : 0);
   int64_t max_tiles = n_tiles * m_tiles_ub;
   if (max_tiles > (1 << 30)) max_tiles = 1 << 30;
 

@@ -9,6 +9,11 @@
 //   smem full[]    : leader only, expect_tx = bytes of BOTH CTAs' loads
 //   smem empty[]   : one per CTA, released by a multicast tcgen05.commit
 //   tmem full[]    : one per CTA (multicast commit); tmem empty[]: leader only, 8 arrivals (4 epilogue warps x 2 CTAs)
+//
+// Pair mode (GemmParams::pair, expert parallelism): the rows live in fixed-capacity regions ordered (expert, source rank); the two
+// CTAs of a pair take 128 rows each from two NEIGHBOURING regions of the same expert, so one weight tile (half staged per CTA) serves
+// both source ranks' rows: half the weight bytes per SM of the 1-CTA kernel, which re-pulled the tile for every region
+// (profiles/r02_gemm_notes.txt).
 #include "gemm_common.cuh"
 
 namespace aria {
@@ -85,8 +90,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = cluster_id;; t += n_clusters) {
         int grp, m_idx, n_idx, row0, rows;
         if (!sched.decode(t, grp, m_idx, n_idx, row0, rows)) break;
-        const int a_row = row0 + m_idx * BM2 + static_cast<int>(rank) * BM;
-        const int bgrp = weight_block(p, grp);
+        // pair mode: this CTA's 128 rows come from ITS region of the super-group; both regions multiply the same expert's weights
+        const int a_row = p.pair ? p.group_offsets[2 * grp + static_cast<int>(rank)] + m_idx * BM
+                                 : row0 + m_idx * BM2 + static_cast<int>(rank) * BM;
+        const int bgrp = weight_block(p, p.pair ? 2 * grp : grp);
         int b_c = 0;
         const CUtensorMap* tb = &tmB0;
         if constexpr (B_MN) {
@@ -185,10 +192,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
-      const int r_in_grp = m_idx * BM2 + r_in_tile;
+      int r_in_grp = m_idx * BM2 + r_in_tile;
+      int my_grp = grp;
+      if (p.pair) {  // rows of this CTA = rows [m_idx * 128, +128) of region 2 grp + rank
+        my_grp = 2 * grp + static_cast<int>(rank);
+        r_in_grp = m_idx * BM + quad * 32 + lane;
+        row0 = p.group_offsets[my_grp];
+        rows = p.group_counts[my_grp];
+      }
       const bool row_ok = r_in_grp < rows;
       const int64_t grow = static_cast<int64_t>(row0) + r_in_grp;
-      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2, grp, r_in_grp);
+      epilogue_tile<BN, EPI>(p, taddr, n_out_total, n_idx, grow, row_ok, (warp - 2) >> 2, my_grp, r_in_grp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tempty0 + as * 8);

@@ -35,6 +35,7 @@ struct GemmParams {
   int b_group_rows;  // K-major grouped weights [G, N, K]: B row of (group g, column c) is g*b_group_rows + c (0: dense)
   int group_mod;  // weight block of group g: g % group_mod (> 0: expert-parallel (source rank, expert) groups), g / -group_mod (< 0:
                   // (expert, source rank) groups - the groups of one expert are neighbours and share its weights in L2), g (0)
+  int pair;       // 2-CTA kernel on fixed-capacity regions: groups (2s, 2s+1) form ONE 256-row tile, 128 rows of each (see gemm2.cu)
   int n_seg;
   int act;
   const __nv_bfloat16* bias[3];
@@ -62,8 +63,10 @@ struct TileSched {
   const int32_t* cnts;
   int G, n_tiles, M;
   int g, mt_prefix, g_row0, g_rows, g_mt, bm;
+  bool pair;
   __device__ void init(const GemmParams& p, int n_tiles_, int bm_ = BM) {
     bm = bm_;
+    pair = p.pair != 0;
     offs = p.group_offsets;
     cnts = p.group_counts;
     G = p.num_groups;
@@ -76,6 +79,13 @@ struct TileSched {
     g_rows = 0;
   }
   __device__ bool load_group(int gi) {
+    if (pair) {  // super-group gi = regions (2 gi, 2 gi + 1); each CTA of the pair walks ITS region in 128-row steps
+      if (2 * gi + 1 >= G) return false;
+      g_row0 = 0;
+      g_rows = max(cnts[2 * gi], cnts[2 * gi + 1]);
+      g_mt = (g_rows + BM - 1) / BM;
+      return true;
+    }
     if (gi >= G) return false;
     if (offs) {
       g_row0 = offs[gi];

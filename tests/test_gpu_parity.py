@@ -169,6 +169,51 @@ def test_grouped_gemm_linearity_full_width():
         assert rel_inf(y[lo:hi], dense) <= REL
 
 
+@pytest.mark.parametrize("W,E_loc,d,I,counts_hi", [(2, 4, 256, 128, 60), (2, 8, 512, 256, 300), (4, 4, 256, 128, 140)])
+def test_expert_parallel_region_gemms_pair_mode(W, E_loc, d, I, counts_hi):
+    """Fixed-capacity regions ordered (expert, source rank) run on CTA PAIRS (two neighbouring regions = one 256-row tile, gemm2.cu
+    pair mode); the same regions addressed in (source rank, expert) order run on the 1-CTA kernel.  Same rows, same weights, same
+    accumulation order per row: the outputs must be bit-identical - fc1 + SwiGLU and fc2 (LINEAR) - and match the oracle."""
+    from aria_b200 import ops
+    from oracle import aria_oracle as O
+    dev = "cuda"
+    g = torch.Generator().manual_seed(11)
+    G, cap = W * E_loc, (counts_hi + 15) // 16 * 16 + 16
+    counts = torch.randint(0, counts_hi + 1, (G,), generator=g).to(torch.int32)
+    counts[1] = 0                       # an empty region next to a populated one
+    counts[2] = counts_hi               # more than 128 rows where counts_hi allows: a second m-tile for one CTA of the pair only
+    starts = torch.arange(G, dtype=torch.int32) * cap
+    a = torch.randn(G * cap, d, generator=g).bfloat16()
+    w1 = (torch.randn(E_loc, d, 2 * I, generator=g) * 0.05).bfloat16()
+    w2 = (torch.randn(E_loc, I, 256, generator=g) * 0.05).bfloat16()
+    # region index (expert-major) el * W + s  <->  (source-major) s * E_loc + el: same memory, other enumeration
+    perm = torch.tensor([(j % E_loc) * W + j // E_loc for j in range(G)])
+    ad, w1d, w2d = a.to(dev), w1.to(dev), w2.to(dev)
+    outs = []
+    for order in ("expert_major", "source_major"):
+        st = (starts if order == "expert_major" else starts[perm]).to(dev).contiguous()
+        ct = (counts if order == "expert_major" else counts[perm]).to(dev).contiguous()
+        gm = -W if order == "expert_major" else E_loc
+        h = torch.zeros(G * cap, I, dtype=torch.bfloat16, device=dev)
+        ops.grouped_gemm_regions(ad, w1d, st, ct, int(counts.sum()), swiglu=True, group_mod=gm, out=h)
+        y = torch.zeros(G * cap, 256, dtype=torch.bfloat16, device=dev)
+        ops.grouped_gemm_regions(h, w2d, st, ct, int(counts.sum()), group_mod=gm, out=y)
+        outs.append((h.cpu(), y.cpu()))
+    torch.cuda.synchronize()
+    for gi in range(G):
+        r0, n = int(starts[gi]), int(counts[gi])
+        if n == 0:
+            continue
+        el = gi // W
+        for t in range(2):
+            assert torch.equal(outs[0][t][r0:r0 + n], outs[1][t][r0:r0 + n]), (gi, t)
+        want_h = O.glu(a[r0:r0 + n] @ w1[el])
+        got_h = outs[0][0][r0:r0 + n].float()
+        assert (got_h - want_h.float()).abs().max() <= 1e-2 * max(1.0, float(want_h.float().abs().max())), gi
+        want_y = (outs[0][0][r0:r0 + n] @ w2[el]).float()
+        assert (outs[0][1][r0:r0 + n].float() - want_y).abs().max() <= 1e-2 * max(1.0, float(want_y.abs().max())), gi
+
+
 @pytest.mark.parametrize("dtype_tag", ["bf16"])
 def test_moe_layer_cfg1_golden(dtype_tag):
     """BASELINE.json configs[0] (d=256, 8 experts, top-2, I=512) against the reference's own outputs."""
