@@ -350,9 +350,11 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
   }
 
   // Expert-parallel regions ordered (expert, source rank) with an even number of source ranks: CTA pairs over neighbouring regions
-  // (gemm2.cu pair mode; ARIA_GEMM_PAIR=0 keeps the 1-CTA kernel for A/B measurements)
+  // (gemm2.cu pair mode).  OPT-IN (ARIA_GEMM_PAIR=1, read per call): isolated it is 11 % faster than the 1-CTA kernel (134 -> 120 us,
+  // half the weight bytes per SM), inside the 2-GPU step it measured 5 % slower (profiles/r02_gemm_notes.txt), so the default stays.
   {
-    static const bool pair_on = [] { const char* e = getenv("ARIA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    const char* pe = getenv("ARIA_GEMM_PAIR");
+    const bool pair_on = pe && pe[0] == '1';
     const bool ok = swiglu ? (d->n % 128 == 0) : (d->n % 256 == 0);
     if (pair_on && d->group_counts && d->group_mod < 0 && (-d->group_mod) % 2 == 0 && b_mn && ok && d->epilogue != ARIA_EPI_HEADS) {
       two_cta = true;

@@ -190,7 +190,9 @@ def test_expert_parallel_region_gemms_pair_mode(W, E_loc, d, I, counts_hi):
     perm = torch.tensor([(j % E_loc) * W + j // E_loc for j in range(G)])
     ad, w1d, w2d = a.to(dev), w1.to(dev), w2.to(dev)
     outs = []
+    old = os.environ.get("ARIA_GEMM_PAIR")
     for order in ("expert_major", "source_major"):
+        os.environ["ARIA_GEMM_PAIR"] = "1" if order == "expert_major" else "0"   # the pair kernel is opt-in (read per call)
         st = (starts if order == "expert_major" else starts[perm]).to(dev).contiguous()
         ct = (counts if order == "expert_major" else counts[perm]).to(dev).contiguous()
         gm = -W if order == "expert_major" else E_loc
@@ -200,6 +202,10 @@ def test_expert_parallel_region_gemms_pair_mode(W, E_loc, d, I, counts_hi):
         ops.grouped_gemm_regions(h, w2d, st, ct, int(counts.sum()), group_mod=gm, out=y)
         outs.append((h.cpu(), y.cpu()))
     torch.cuda.synchronize()
+    if old is None:
+        os.environ.pop("ARIA_GEMM_PAIR", None)
+    else:
+        os.environ["ARIA_GEMM_PAIR"] = old
     for gi in range(G):
         r0, n = int(starts[gi]), int(counts[gi])
         if n == 0:
