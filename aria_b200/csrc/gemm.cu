@@ -338,12 +338,18 @@ extern "C" int aria_gemm(const aria_gemm_desc_t* d, aria_stream_t stream_) {
     const bool divisible = swiglu ? (d->n % 128 == 0) : ((d->n_seg == 1 && !b_gnk) || d->n % 256 == 0);
     const int64_t m_tiles256 = (d->num_groups == 1) ? (d->m + 255) / 256 : (d->m / 256 + d->num_groups / 2);
     const int64_t tiles256 = m_tiles256 * ((n_out_total + out_bn256 - 1) / out_bn256);
-    static const int mid = [] { const char* e = getenv("ARIA_GEMM_MID"); return e ? atoi(e) : 0; }();
-    if (divisible && tiles256 * 10 >= 13 * (sm_count() / 2)) {
+    static const int mid = [] { const char* e = getenv("ARIA_GEMM_MID"); return e ? atoi(e) : 1; }();
+    // short-K dense GEMMs whose 256 x 256 tiles fill the last round badly run better as 128 x 128 tiles: ViT o_proj
+    // (4900 x 1152 x 1152: 100 pair tiles on 74 pairs = 0.68 of two rounds) 27.4 us on pairs, 23.3 us on single CTAs; with a long K
+    // (ViT fc2, K = 4304, same tile count) the pair kernel stays ahead (57.9 vs 66.7 us).  profiles/r02_gemm_notes.txt
+    const int64_t pairs = sm_count() / 2;
+    const double fill2 = static_cast<double>(tiles256) / static_cast<double>((tiles256 + pairs - 1) / pairs * pairs);
+    const bool poor_fill = d->num_groups == 1 && d->k <= 2048 && fill2 < 0.75;
+    if (divisible && tiles256 * 10 >= 13 * pairs && !poor_fill) {
       BN = 256;
-    } else if (mid && d->num_groups == 1 && d->m >= 256) {
-      // mid-size dense GEMM (e.g. the T=768 LM projections): 256 x 128 pair tiles pull 24 KB per CTA per k-block from
-      // L2 instead of 32 KB (ARIA_GEMM_MID=1, A/B switch)
+    } else if (mid && d->num_groups == 1 && d->m >= 256 && d->m <= 1024) {
+      // mid-size dense GEMM (the T=768 LM projections): 256 x 128 pair tiles pull 24 KB per CTA per k-block from L2 instead of
+      // 32 KB: qkv+RoPE 37.4 -> 33.7 us, shared gate|up 32.8 -> 29.2, o_proj 19.7 -> 19.2, down 19.0 -> 18.2 (ARIA_GEMM_MID=0 disables)
     } else {
       two_cta = false;
     }
