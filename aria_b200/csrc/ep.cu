@@ -40,7 +40,7 @@ __global__ void peer_barrier_kernel(const uint64_t* __restrict__ peer_flags, int
   int v;
   do {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    if (clock64() - t0 > 20000000000ll) {
+    if (clock64() - t0 > 80000000000ll) {  // ~40 s: ranks can be seconds apart at the first barrier (lazy module loads), never minutes
       printf("aria_b200: peer barrier timeout (rank %d waiting for %d, epoch %d, saw %d)\n", rank, s, epoch, v);
       __trap();
     }
