@@ -262,6 +262,27 @@ __global__ void __launch_bounds__(1024) merge_kernel(const int64_t* __restrict__
   if (threadIdx.x == 0 && count_out) *count_out = running_s;
 }
 
+// Multi-block variant for prompts of up to 16384 tokens: one warp per token; a warp whose token is an image slot counts the
+// image tokens in front of it (lanes stride over ids[0..t)) to find its feature row, then copies the row.  The single-block kernel
+// above copies the 256 x 5 KB rows of a cfg-2 prompt with ONE SM: 86 us per step in profiles/r02_launch_shares_final.txt.
+__global__ void __launch_bounds__(256) merge_rows_kernel(const int64_t* __restrict__ ids, int64_t image_token,
+                                                         const uint4* __restrict__ feats, uint4* __restrict__ embeds,
+                                                         int32_t* __restrict__ count_out, int64_t n, int vpr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (t >= n) return;
+  const bool hit = ids[t] == image_token;
+  const bool last = t == n - 1;
+  if (!hit && !(last && count_out)) return;
+  int c = 0;
+  for (int64_t i = lane; i < t; i += 32) c += ids[i] == image_token;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (hit)
+    for (int v = lane; v < vpr; v += 32) embeds[t * vpr + v] = __ldg(feats + static_cast<int64_t>(c) * vpr + v);
+  if (last && count_out && lane == 0) *count_out = c + (hit ? 1 : 0);
+}
+
 // patches[(b*Np + py*Nside + px), c*P*P + i*P + j] = pixels[b, c, py*P + i, px*P + j]; k_pad zero padded.
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ pix, __nv_bfloat16* __restrict__ out, int B, int S, int P,
                               int k_pad) {
@@ -377,6 +398,11 @@ extern "C" int aria_merge_image_features(const int64_t* ids, int64_t image_token
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ARIA_CHECK_ARG(ids && features && embeds && d % 8 == 0 && n >= 0);
   if (n == 0) return ARIA_OK;
+  if (n <= 16384) {
+    merge_rows_kernel<<<static_cast<int>((n + 7) / 8), 256, 0, stream>>>(ids, image_token, static_cast<const uint4*>(features),
+                                                                         static_cast<uint4*>(embeds), count_out, n, d / 8);
+    return check_launch("merge_rows_kernel");
+  }
   merge_kernel<<<1, 1024, 0, stream>>>(ids, image_token, static_cast<const uint4*>(features), static_cast<uint4*>(embeds),
                                        count_out, n, d / 8);
   return check_launch("merge_kernel");

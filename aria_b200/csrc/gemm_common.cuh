@@ -319,25 +319,33 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
         }
       }
     } else {
-      constexpr int NCH = (BN + 31) / 32;
-      const int cb = (half * NCH / 2) * 32, ce = half ? NCH * 32 : (NCH / 2) * 32;
-#pragma unroll 1
-      for (int c = cb; c < ce; c += 32) {
-        uint32_t v[32];
-        if (c + 32 <= BN) {
-          tmem_ld_32x32(taddr + c, v);
-        } else {  // BN not a multiple of 32 (e.g. 144): the tail re-reads an overlapping window
-          tmem_ld_32x32(taddr + BN - 32, v);
-        }
-        const int cbase = (c + 32 <= BN) ? c : BN - 32;
-        const int qstart = (c + 32 <= BN) ? 0 : (c - cbase) / 8;
-        uint4 bvq[4];  // the chunk's bias vectors, requested before the TMEM wait
+      constexpr int NCH = (BN + 31) / 32, NMAX = NCH - NCH / 2;
+      const int cb = half ? (NCH / 2) * 32 : 0;
+      const int n_my = half ? NCH - NCH / 2 : NCH / 2;
+      // same two-deep pipeline as the LINEAR epilogue: accumulator chunk and bias vectors of chunk i + 1 in flight while chunk i
+      // is converted and scattered to its heads
+      uint32_t v[2][32];
+      uint4 bvq[2][4];
+      auto window = [&](int c) { return (c + 32 <= BN) ? c : BN - 32; };  // BN = 144: the tail re-reads an overlapping window
+      auto issue = [&](int c, int set) {
+        const int cbase = window(c);
+        tmem_ld_32x32(taddr + cbase, v[set]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int cs_ = cseg0 + cbase + q * 8;
-          bvq[q] = (bias && cs_ + 8 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(bias + cs_)) : make_uint4(0, 0, 0, 0);
+          bvq[set][q] = (bias && cs_ + 8 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(bias + cs_)) : make_uint4(0, 0, 0, 0);
         }
+      };
+      if (n_my > 0) issue(cb, 0);
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        if (i >= n_my) break;
+        const int c = cb + i * 32;
+        const int set = i & 1;
         tmem_ld_wait();
+        if (i + 1 < n_my) issue(c + 32, set ^ 1);
+        const int cbase = window(c);
+        const int qstart = (c + 32 <= BN) ? 0 : (c - cbase) / 8;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q < qstart) continue;
@@ -345,9 +353,9 @@ ARIA_DEVICE void epilogue_tile(const GemmParams& p, const uint32_t taddr, const 
           if (cs_ + 8 > p.N) continue;
           float x[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[q * 8 + j]);
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[set][q * 8 + j]);
           if (bias) {
-            const uint4 bv = bvq[q];
+            const uint4 bv = bvq[set][q];
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
