@@ -69,6 +69,10 @@ def test_op_work_models_match_survey_8d():
     assert abs(fl / (5120 * 768 * 768) - 1) < 2e-3
     _, fl, by = b.op_work("linear", (meta(768, 2560), meta(2560, 2560)), {})
     assert fl == 2 * 768 * 2560 * 2560 and by == 2 * (768 * 2560 * 2 + 2560 * 2560)
+    # expert parallelism: the fc1 GEMM of ONE rank of 8 (8 local experts, rows of all ranks in fixed-capacity regions)
+    lab, fl, by = b.op_work("grouped_gemm_regions", (meta(64 * 784, 2560), meta(8, 2560, 3328), meta(64, dt=torch.int32),
+                                                     meta(64, dt=torch.int32), 4608), {"swiglu": True, "group_mod": -8})
+    assert "E8local" in lab and fl == 2 * 4608 * 2560 * 3328 and by == 2 * (8 * 2560 * 3328 + 4608 * 2560 + 4608 * 1664)
 
 
 def test_kernel_table_picks_the_dominant_kernel_by_share():
