@@ -92,3 +92,14 @@ def test_kernel_table_picks_the_dominant_kernel_by_share():
     assert rows[0]["kernel"] == "attention[x]" and rows[0]["bound"] == "tensor" and abs(rows[0]["share"] - 0.4) < 1e-9
     assert abs(rows[0]["achieved"] - 553.0) < 1.0 and abs(rows[0]["frac"] - 553.0 / 1480.4) < 1e-3
     assert rows[1]["bound"] == "hbm" and abs(rows[1]["achieved"] - 1.1e9 / 0.15 / 1e6) < 1e-6
+
+
+def test_dominant_kernels_have_committed_dram_traffic():
+    """`roofline.traffic` comes from committed ncu captures (profiles/kernel_traffic.json): present for the two kernels that can be the
+    largest share of the cfg-2 step, and within 1.6x of their algorithmic bytes (no wasted re-reads)."""
+    b = _bench()
+    t_attn = b._traffic_for("attention[full,B1xH16,Tq4900,Tk4900,hd72]")
+    t_fc1 = b._traffic_for("grouped_gemm_swiglu[4608rows,E64,2560->3328]")
+    assert t_attn and t_fc1 and b._traffic_for("no_such_kernel[1]") is None
+    assert 45158400 <= t_attn <= 1.6 * 45158400          # q, k, v, out of 16 heads x 4900 x 72 (+ stream-K pieces)
+    assert 1129447424 * 0.98 <= t_fc1 <= 1.05 * 1129447424
