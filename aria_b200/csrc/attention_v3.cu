@@ -18,6 +18,10 @@
 //     (O, m, l) merged by attn_merge_kernel — 320 units on 148 SMs take 2.17 rounds instead of 3.
 //   Causal launches (LM prefill) keep one unit per CTA, heaviest first (the hardware block scheduler is the LPT list
 //   scheduler there).
+// Where it stands (profiles/r02_attention_notes.txt): 185-192 us on that shape = 0.39-0.40 of the sustained tensor peak on real
+// FLOPs.  ncu: MUFU pipe 56 %, tensor pipe 35 %: each tile is a serial chain S -> softmax -> P -> PV -> QK whose fixed latencies
+// (five barrier hand-offs, TMEM load / store round trips), not a pipe, set the 3310-clk period per 256 x 128 block.  The share of
+// exponentials on the FMA pipe (ARIA_ATTN_POLY) therefore stays 0: it measured slower (+40 % instructions for -25 % MUFU).
 #include <stdlib.h>
 
 #include "common.cuh"
